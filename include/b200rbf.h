@@ -1,0 +1,142 @@
+/*
+ * b200rbf.h -- C ABI of libb200rbf.so: pySOT's RBF-surrogate hot path on one B200 (sm_100a).
+ *
+ * Drop-in boundary.  The reference is pure Python; its "FFI" for this path is the set of
+ * numpy/scipy calls made by pySOT/surrogate/rbf.py and pySOT/auxiliary_problems/candidate_srbf.py.
+ * Each entry point below names the reference lines it replaces (paths relative to the pySOT tree).
+ * The Python side (pysot_b200/_lib.py) binds these with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative B200RBF_E* code on failure; it never throws,
+ *     aborts or exits.  b200rbf_last_error() returns a thread-local message for the last failure.
+ *   - all floating-point data is IEEE fp64, matrices are C-contiguous row-major.
+ *   - data pointers may be HOST or DEVICE pointers (told apart with cudaPointerGetAttributes); host
+ *     inputs are staged through pinned buffers and overlapped with compute, outputs are caller
+ *     allocated.  Pointers documented "dev" must be device memory (e.g. a torch tensor's data_ptr()).
+ *   - a handle is bound to one device and is NOT thread-safe (pySOT drives the surrogate from the
+ *     single POAP controller thread); calls are ordered on the handle's stream and synchronise before
+ *     returning anything to host memory.
+ *   - there is no CPU fallback: without a CUDA device b200rbf_create fails.
+ */
+#ifndef B200RBF_H
+#define B200RBF_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200rbf_ctx* b200rbf_handle;
+
+/* kernels: pySOT/surrogate/kernels/{cubic,tps,linear}_kernel.py ; tails: surrogate/tails/{linear,constant}_tail.py */
+enum { B200RBF_KERNEL_CUBIC = 0, B200RBF_KERNEL_TPS = 1, B200RBF_KERNEL_LINEAR = 2 };
+enum { B200RBF_TAIL_LINEAR = 0, B200RBF_TAIL_CONSTANT = 1 };
+
+enum {
+  B200RBF_OK = 0,
+  B200RBF_EINVAL = -1,    /* bad argument (reference: ValueError / AssertionError) */
+  B200RBF_ECUDA = -2,     /* CUDA runtime failure */
+  B200RBF_ESTATE = -3,    /* call order: no model loaded / nothing scored */
+  B200RBF_ESINGULAR = -4, /* exactly singular pivot in the saddle-point LU */
+  B200RBF_ENOMEM = -5
+};
+
+/* options for b200rbf_set_option */
+enum {
+  /* 1: squared distances use separate multiply and add, sequentially over the coordinates -- bit-identical
+   *    to scipy's cdist (rbf.py:181, candidate_srbf.py:35).  0 (default): fused multiply-add.           */
+  B200RBF_OPT_EXACT_DIST = 1,
+  /* rows per host->device chunk of the candidate pipeline (default 65536)                              */
+  B200RBF_OPT_CHUNK_ROWS = 2,
+  /* LU panel width (default 128; multiple of 32)                                                       */
+  B200RBF_OPT_LU_PANEL = 3
+};
+
+const char* b200rbf_last_error(void);
+int b200rbf_version(void);
+
+/* Lifetime.  device = CUDA ordinal.  The handle owns resident centers / coefficients / LU workspace /
+ * candidate workspace until destroy. */
+int b200rbf_create(int device, b200rbf_handle* out);
+int b200rbf_destroy(b200rbf_handle h);
+/* cudaStream_t to enqueue on (e.g. torch.cuda.current_stream().cuda_stream); NULL = handle's own stream. */
+int b200rbf_set_stream(b200rbf_handle h, void* cuda_stream);
+int b200rbf_set_option(b200rbf_handle h, int option, long long value);
+
+/* RBFInterpolant._fit, initial branch + coefficient solve (rbf.py:110-130, 164-168):
+ *   A = [[0, P^T], [P, phi(cdist(Xu, Xu)) + eta I]],  c = A^-1 [0; rhs]   by LU with partial pivoting.
+ * Xu: n x d centers already mapped to the unit box (surrogate.py:71); rhs: n transformed values
+ * (output_transformation(fX), rbf.py:164).  c_out: n + ntail coefficients, tail first (rbf.py:183-184),
+ * ntail = d + 1 (linear tail) or 1 (constant).  Centers and coefficients stay resident for predict /
+ * predict_deriv / score.  Requires n >= ntail (rbf.py:111) and kernel order - 1 <= tail degree (rbf.py:85).
+ * fit_seconds (optional): device time of assembly + factorisation + solves (CUDA events). */
+int b200rbf_fit(b200rbf_handle h, const double* Xu, const double* rhs, int n, int d, int kernel, int tail,
+                double eta, double* c_out, double* fit_seconds);
+
+/* Make centers + coefficients resident without fitting (replica GPUs of the sharded scoring path, or a
+ * model restored from a pickle).  c: n + ntail, tail first. */
+int b200rbf_load(b200rbf_handle h, const double* Xu, const double* c, int n, int d, int kernel, int tail);
+
+/* RBFInterpolant.predict (rbf.py:170-185).  x: m x d points in ORIGINAL coordinates; lb, ub: d host
+ * doubles (to_unit_box is applied on the device, utils.py:33).  out: m values. */
+int b200rbf_predict(b200rbf_handle h, const double* x, long long m, const double* lb, const double* ub, double* out);
+
+/* RBFInterpolant.predict_deriv (rbf.py:187-215).  out: m x d gradients w.r.t. original coordinates. */
+int b200rbf_predict_deriv(b200rbf_handle h, const double* x, long long m, const double* lb, const double* ub,
+                          double* out);
+
+/* First half of weighted_distance_merit (candidate_srbf.py:31-40): one fused pass computes
+ *   fvals[i]  = surrogate.predict(cand[i])                        (unit-box metric, rbf.py:180-185)
+ *   dmerit[i] = min_j || cand[i] - Xdist[j] ||_2                  (ORIGINAL metric, candidate_srbf.py:35-36)
+ * and their global min / max (unit_rescale, utils.py:60-65).  Xdist = vstack(X, Xpend), ndist rows.
+ * alias_centers != 0 promises that the first n rows of Xdist are the resident centers in original
+ * coordinates (true under every pySOT strategy, surrogate_strategy.py:427-429); with an isotropic box the
+ * kernel then derives both metrics from one distance.  cand / fvals / dmerit stay resident for select.
+ * fvals_out / dmerit_out (optional, m each) and stats_out (optional, host, {fmin,fmax,dmin,dmax}). */
+int b200rbf_score(b200rbf_handle h, const double* cand, long long m, const double* lb, const double* ub,
+                  const double* Xdist, int ndist, int alias_centers, double* fvals_out, double* dmerit_out,
+                  double* stats_out);
+
+/* Second half of weighted_distance_merit (candidate_srbf.py:43-55) on the resident scores: for i < p
+ *   merit = w_i * fhat + (1 - w_i) * (1 - dhat);  merit[dmerit < dtol] = inf;  jj = first argmin;
+ *   fvals[jj] = inf;  dmerit = minimum(dmerit, || cand - cand[jj] ||).
+ * idx_out: p selected row indices into cand; merit_out (optional): their merit values. */
+int b200rbf_select(b200rbf_handle h, const double* weights, int p, double dtol, long long* idx_out,
+                   double* merit_out);
+
+/* ---- phase API for candidates sharded over several GPUs (one process and one handle per GPU).  The
+ * caller reduces the tiny device buffers between phases with NCCL (torch.distributed):
+ *   stats_dev  : 4 doubles {fmin, -fmax, dmin, -dmax}  -> all-reduce(MIN)
+ *   pair_dev   : 2 x 8 bytes {double merit, int64 global_index} -> all-gather, lowest (merit, index) wins
+ *   winner_dev : d doubles, the winning candidate row -> broadcast from its owner
+ */
+/* copy the local stats (after b200rbf_score or b200rbf_shard_update) into stats_dev in the layout above */
+int b200rbf_shard_stats(b200rbf_handle h, double* stats_dev);
+/* local merit + argmin using the (globally reduced) stats_dev; writes pair_dev; index = local + idx_offset */
+int b200rbf_shard_argmin(b200rbf_handle h, double w, double dtol, const double* stats_dev, long long idx_offset,
+                         void* pair_dev);
+/* copy resident candidate row local_idx into winner_dev and mark fvals[local_idx] = inf (owner only) */
+int b200rbf_shard_take(b200rbf_handle h, long long local_idx, double* winner_dev);
+/* dmerit = minimum(dmerit, || cand - winner ||) on the local shard; refreshes the local dmin / dmax */
+int b200rbf_shard_update(b200rbf_handle h, const double* winner_dev);
+
+/* Measured FP64 ceilings of this device, used as roofline denominators by bench.py: a dependent-free
+ * DFMA loop and an mma.sync m8n8k4 f64 (DMMA) loop, full grid, `ms` milliseconds each.
+ * out[0] = DFMA TFLOP/s, out[1] = DMMA TFLOP/s. */
+int b200rbf_fp64_peaks(b200rbf_handle h, double ms, double* out);
+
+/* Counters: number of kernels this handle launched since creation (bench.py's gpu_launches). */
+long long b200rbf_launch_count(b200rbf_handle h);
+
+/* ---- test hooks: exercise the factorisation pieces in isolation (tests/ only, not the drop-in surface) ----
+ * dbg_lu  : A_host is N x (N + nrhs) row-major; on return the leading N x N block holds L\U (unit lower L),
+ *           the extra columns hold L^-1 P b, ipiv_host the LAPACK-style 0-based pivot rows, info the first
+ *           exactly-zero pivot (1-based) or 0.                                  (scipy.linalg.lu_factor, rbf.py:123)
+ * dbg_gemm: C (M x Nc) -= A (M x K) * B (K x Nc) on the FP64 tensor cores; K % 16 == 0. */
+int b200rbf_dbg_lu(b200rbf_handle h, double* A_host, int N, int nrhs, int* ipiv_host, int* info);
+int b200rbf_dbg_gemm(b200rbf_handle h, double* C_host, const double* A_host, const double* B_host, int M, int Nc,
+                     int K, double* seconds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RBF_H */

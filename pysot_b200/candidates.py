@@ -1,0 +1,200 @@
+"""Candidate-search acquisition on the GPU behind the reference's function signatures.
+
+  weighted_distance_merit   pySOT/auxiliary_problems/candidate_srbf.py:8-57
+  candidate_srbf            pySOT/auxiliary_problems/candidate_srbf.py:60-121
+  candidate_dycors          pySOT/auxiliary_problems/candidate_dycors.py:8-94
+  candidate_uniform         pySOT/auxiliary_problems/candidate_uniform.py:7-53
+
+Candidate GENERATION stays on the host and consumes the global numpy RNG and scipy's truncnorm in exactly the
+reference's call order, so a seeded run proposes bit-identical candidate sets (north star: "host-generated
+candidate sets").  SCORING and SELECTION (the m x n work) run in libb200rbf.so: one fused pass for surrogate
+value + min distance + min/max statistics, then the merit / argmin / distance-update loop on the device.
+
+``install()`` rebinds the names the reference's strategy modules bound at import time, so SRBFStrategy,
+DYCORSStrategy and SOPStrategy use these functions unchanged.
+"""
+import numpy as np
+import scipy.stats as stats
+
+from .rbf import GpuRBFInterpolant
+
+
+def _round_vars(x, int_var, lb, ub):
+    """pySOT/utils.py:68-93 (in place)."""
+    if len(int_var) > 0:
+        x[:, int_var] = np.round(x[:, int_var])
+        for i in int_var:
+            x[np.where(x[:, i] < lb[i]), i] = lb[i]
+            x[np.where(x[:, i] > ub[i]), i] = ub[i]
+    return x
+
+
+def weighted_distance_merit(num_pts, surrogate, X, fX, cand, weights, Xpend=None, dtol=1e-3):
+    """Pick ``num_pts`` rows of ``cand`` by the weighted-distance merit (candidate_srbf.py:8-57).
+
+    Returns a ``(num_pts, dim)`` float64 array of rows copied from ``cand``.
+    """
+    if not isinstance(surrogate, GpuRBFInterpolant):
+        raise TypeError("pysot_b200.weighted_distance_merit needs a GpuRBFInterpolant (there is no CPU fallback); got %r"
+                        % type(surrogate).__name__)
+    idx = merit_select_indices(num_pts, surrogate, X, cand, weights, Xpend, dtol)[0]
+    return np.asarray(cand, dtype=np.float64)[idx, :].copy()
+
+
+def merit_select_indices(num_pts, surrogate, X, cand, weights, Xpend=None, dtol=1e-3, want_scores=False):
+    """The device part of weighted_distance_merit.  Returns (indices, merit values[, fvals, dmerit, stats])."""
+    X = np.asarray(X, dtype=np.float64)
+    dim = X.shape[1]
+    cand = np.asarray(cand, dtype=np.float64)
+    if cand.ndim != 2 or cand.shape[1] != dim:
+        raise ValueError("XA and XB must have the same number of columns (i.e. feature dimension.)")  # cdist's message
+    if Xpend is None:
+        Xpend = np.empty([0, dim])  # candidate_srbf.py:33-34
+    Xdist = np.vstack((X, Xpend))
+    if Xdist.shape[0] == 0:
+        raise ValueError("zero-size array to reduction operation minimum which has no identity")  # np.amin, :36
+    surrogate._fit()  # predict() would do this at candidate_srbf.py:39
+    # Under the strategies the surrogate's points are exactly X (surrogate_strategy.py:427-429); then one
+    # distance serves both metrics.  extra_points (surrogate_strategy.py:243-247) break the aliasing.
+    alias = X.shape == surrogate.X.shape and np.array_equal(X, surrogate.X)
+    h = surrogate.handle
+    fv, dm, st = h.score(cand, surrogate.lb, surrogate.ub, Xdist, alias, want_scores=want_scores)
+    idx, merit = h.select(weights, num_pts, dtol)
+    if want_scores:
+        return idx, merit, fv, dm, st
+    return idx, merit
+
+
+def _prepare(opt_prob, X, fX, subset, num_cand, xbest=None):
+    if xbest is None:
+        xbest = np.copy(X[np.argmin(fX), :]).ravel()
+    if num_cand is None:
+        num_cand = 100 * opt_prob.dim
+    if subset is None:
+        subset = np.arange(0, opt_prob.dim)
+    return xbest, num_cand, subset
+
+
+def _scale_factors(opt_prob, sampling_radius, subset):
+    """sigma per coordinate, at least 1 for integer variables (candidate_srbf.py:100-103)."""
+    sf = sampling_radius * (opt_prob.ub - opt_prob.lb)
+    ind = np.intersect1d(opt_prob.int_var, subset)
+    if len(ind) > 0:
+        sf[ind] = np.maximum(sf[ind], 1.0)
+    return sf
+
+
+def generate_srbf(opt_prob, X, fX, sampling_radius=0.2, subset=None, num_cand=None):
+    """Truncated-normal perturbation of every coordinate in ``subset`` around xbest (candidate_srbf.py:91-116)."""
+    xbest, num_cand, subset = _prepare(opt_prob, X, fX, subset, num_cand)
+    sf = _scale_factors(opt_prob, sampling_radius, subset)
+    cand = np.multiply(np.ones((num_cand, opt_prob.dim)), xbest)
+    for i in subset:
+        lo, hi, s = opt_prob.lb[i], opt_prob.ub[i], sf[i]
+        cand[:, i] = stats.truncnorm.rvs(a=(lo - xbest[i]) / s, b=(hi - xbest[i]) / s, loc=xbest[i], scale=s,
+                                         size=num_cand)
+    return _round_vars(cand, opt_prob.int_var, opt_prob.lb, opt_prob.ub)
+
+
+def generate_dycors(opt_prob, X, fX, prob_perturb, sampling_radius=0.2, subset=None, num_cand=None, xbest=None):
+    """DYCORS perturbation (candidate_dycors.py:55-89): each coordinate of ``subset`` is perturbed with
+    probability ``prob_perturb``; rows with no perturbed coordinate get one at ``randint(0, len(subset) - 1)``
+    (upper bound exclusive, so never the last one -- reference behaviour, kept for seeded parity, :78).  The mask
+    column is indexed by ``i`` while the value is written to ``subset[i]`` (:83-84), also kept."""
+    xbest, num_cand, subset = _prepare(opt_prob, X, fX, subset, num_cand, xbest)
+    sf = _scale_factors(opt_prob, sampling_radius, subset)
+    if len(subset) == 1:
+        ar = np.ones((num_cand, 1))
+    else:
+        ar = np.random.rand(num_cand, len(subset)) < prob_perturb
+        ind = np.where(np.sum(ar, axis=1) == 0)[0]
+        ar[ind, np.random.randint(0, len(subset) - 1, size=len(ind))] = 1
+    cand = np.multiply(np.ones((num_cand, opt_prob.dim)), xbest)
+    for i in subset:
+        lo, hi, s = opt_prob.lb[i], opt_prob.ub[i], sf[i]
+        ind = np.where(ar[:, i] == 1)[0]
+        cand[ind, subset[i]] = stats.truncnorm.rvs(a=(lo - xbest[i]) / s, b=(hi - xbest[i]) / s, loc=xbest[i],
+                                                   scale=s, size=len(ind))
+    return _round_vars(cand, opt_prob.int_var, opt_prob.lb, opt_prob.ub)
+
+
+def generate_uniform(opt_prob, X, fX, subset=None, num_cand=None):
+    """Uniform candidates in the box on ``subset``, xbest elsewhere (candidate_uniform.py:34-48)."""
+    xbest, num_cand, subset = _prepare(opt_prob, X, fX, subset, num_cand)
+    cand = np.multiply(np.ones((num_cand, opt_prob.dim)), xbest)
+    cand[:, subset] = np.random.uniform(opt_prob.lb[subset], opt_prob.ub[subset], (num_cand, len(subset)))
+    return _round_vars(cand, opt_prob.int_var, opt_prob.lb, opt_prob.ub)
+
+
+def candidate_srbf(num_pts, opt_prob, surrogate, X, fX, weights, Xpend=None, sampling_radius=0.2, subset=None,
+                   dtol=1e-3, num_cand=None):
+    """candidate_srbf.py:60-121."""
+    cand = generate_srbf(opt_prob, X, fX, sampling_radius, subset, num_cand)
+    return weighted_distance_merit(num_pts=num_pts, surrogate=surrogate, X=X, fX=fX, Xpend=Xpend, cand=cand,
+                                   dtol=dtol, weights=weights)
+
+
+def candidate_dycors(num_pts, opt_prob, surrogate, X, fX, weights, prob_perturb, Xpend=None, sampling_radius=0.2,
+                     subset=None, dtol=1e-3, num_cand=None, xbest=None):
+    """candidate_dycors.py:8-94."""
+    cand = generate_dycors(opt_prob, X, fX, prob_perturb, sampling_radius, subset, num_cand, xbest)
+    return weighted_distance_merit(num_pts=num_pts, surrogate=surrogate, X=X, fX=fX, Xpend=Xpend, cand=cand,
+                                   dtol=dtol, weights=weights)
+
+
+def candidate_uniform(num_pts, opt_prob, surrogate, X, fX, weights, Xpend=None, subset=None, dtol=1e-3,
+                      num_cand=None):
+    """candidate_uniform.py:7-53."""
+    cand = generate_uniform(opt_prob, X, fX, subset, num_cand)
+    return weighted_distance_merit(num_pts=num_pts, surrogate=surrogate, X=X, fX=fX, Xpend=Xpend, cand=cand,
+                                   dtol=dtol, weights=weights)
+
+
+# ---------------------------------------------------------------------------------------------- install / uninstall
+# (module, attribute) pairs bound at import time in the reference:
+#   srbf_strategy.py:6, dycors_strategy.py:5, sop_strategy.py:7, auxiliary_problems/__init__.py:2-4,
+#   candidate_dycors.py:5, candidate_uniform.py:4, candidate_srbf.py:8
+_BINDINGS = [
+    ("pySOT.strategy.srbf_strategy", "candidate_srbf"),
+    ("pySOT.strategy.dycors_strategy", "candidate_dycors"),
+    ("pySOT.strategy.sop_strategy", "candidate_dycors"),
+    ("pySOT.auxiliary_problems", "candidate_srbf"),
+    ("pySOT.auxiliary_problems", "candidate_dycors"),
+    ("pySOT.auxiliary_problems", "candidate_uniform"),
+    ("pySOT.auxiliary_problems", "weighted_distance_merit"),
+    ("pySOT.auxiliary_problems.candidate_srbf", "weighted_distance_merit"),
+    ("pySOT.auxiliary_problems.candidate_srbf", "candidate_srbf"),
+    ("pySOT.auxiliary_problems.candidate_dycors", "weighted_distance_merit"),
+    ("pySOT.auxiliary_problems.candidate_dycors", "candidate_dycors"),
+    ("pySOT.auxiliary_problems.candidate_uniform", "weighted_distance_merit"),
+    ("pySOT.auxiliary_problems.candidate_uniform", "candidate_uniform"),
+]
+_saved = {}
+
+
+def install():
+    """Rebind pySOT's candidate functions to the GPU versions.  Returns the list of names rebound."""
+    import importlib
+
+    mine = globals()
+    done = []
+    for modname, attr in _BINDINGS:
+        try:
+            mod = importlib.import_module(modname)
+        except Exception:
+            continue
+        if not hasattr(mod, attr) or getattr(mod, attr) is mine[attr]:
+            continue
+        _saved[(modname, attr)] = getattr(mod, attr)
+        setattr(mod, attr, mine[attr])
+        done.append("%s.%s" % (modname, attr))
+    return done
+
+
+def uninstall():
+    """Restore what ``install`` replaced."""
+    import importlib
+
+    for (modname, attr), fn in list(_saved.items()):
+        setattr(importlib.import_module(modname), attr, fn)
+        del _saved[(modname, attr)]

@@ -1,0 +1,677 @@
+// C ABI of libb200rbf.so (include/b200rbf.h): argument checking, host<->device staging, stream ordering.
+#include <stdarg.h>
+
+#include "score_kernels.cuh"
+
+namespace b200rbf {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int deriv_scratch_doubles(const b200rbf_ctx* h, long long m, size_t* out);
+int run_lu_debug(b200rbf_ctx* h, double* A_dev, int ld, int N, int rcol0, int ncols, int* ipiv_dev, int* info_dev);
+int run_gemm_debug(b200rbf_ctx* h, double* C, int ldc, const double* A, int lda, const double* B, int ldb, int M,
+                   int Nc, int K);
+
+namespace {
+
+enum PtrKind { kPageable = 0, kPinned = 1, kDevice = 2 };
+PtrKind ptr_kind(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return kPageable;
+  }
+  if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) return kDevice;
+  if (at.type == cudaMemoryTypeHost) return kPinned;
+  return kPageable;
+}
+
+// copy `bytes` from a host-or-device source into device memory, ordered on h->stream
+int copy_in(b200rbf_ctx* h, void* dst_dev, const void* src, size_t bytes) {
+  if (bytes == 0) return 0;
+  const PtrKind k = ptr_kind(src);
+  B2_CUDA(cudaMemcpyAsync(dst_dev, src, bytes, k == kDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                          h->stream));
+  return 0;
+}
+int copy_out(b200rbf_ctx* h, void* dst, const void* src_dev, size_t bytes) {
+  if (bytes == 0) return 0;
+  const PtrKind k = ptr_kind(dst);
+  B2_CUDA(cudaMemcpyAsync(dst, src_dev, bytes, k == kDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                          h->stream));
+  return 0;
+}
+
+__global__ void pad_points_kernel(const double* __restrict__ src, int n, int d, double* __restrict__ dst, int npad,
+                                  int dpad) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)npad * dpad) return;
+  const int i = (int)(e / dpad), k = (int)(e - (long long)i * dpad);
+  const int si = i < n ? i : n - 1;  // pad rows repeat the last point: no effect on a min, weight 0 in a sum
+  dst[e] = k < d ? src[(size_t)si * d + k] : 0.0;
+}
+__global__ void split_coef_kernel(const double* __restrict__ c, int t, int n, double* __restrict__ coef, int npad,
+                                  double* __restrict__ tailc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < npad) coef[i] = i < n ? c[t + i] : 0.0;
+  if (i < t) tailc[i] = c[i];
+}
+__global__ void negate_stats_kernel(const double* __restrict__ s, double* __restrict__ out) {
+  if (threadIdx.x == 0) {
+    out[0] = s[0];
+    out[1] = -s[1];
+    out[2] = s[2];
+    out[3] = -s[3];
+  }
+}
+
+int check_model_args(int n, int d, int kernel, int tail) {
+  B2_CHECK(n >= 1 && d >= 1, B200RBF_EINVAL, "n and d must be positive (n=%d, d=%d)", n, d);
+  B2_CHECK(kernel >= 0 && kernel <= 2, B200RBF_EINVAL, "unknown kernel id %d", kernel);
+  B2_CHECK(tail >= 0 && tail <= 1, B200RBF_EINVAL, "unknown tail id %d", tail);
+  // rbf.py:85-86: kernel.order - 1 > tail.degree  ->  ValueError("Kernel and tail mismatch")
+  const int order = (kernel == B200RBF_KERNEL_LINEAR) ? 1 : 2;
+  const int degree = (tail == B200RBF_TAIL_LINEAR) ? 1 : 0;
+  B2_CHECK(order - 1 <= degree, B200RBF_EINVAL, "Kernel and tail mismatch");
+  B2_CHECK(pad_dim(d) <= kMaxRegDim, B200RBF_EINVAL, "dim %d > %d is not supported by this build", d, kMaxRegDim);
+  return 0;
+}
+
+// make Xu (n x d, device) and c (n + t, device) the resident model
+int install_model(b200rbf_ctx* h, const double* Xu_dev, const double* c_dev, int n, int d, int kernel, int tail) {
+  Model& M = h->model;
+  M.loaded = false;
+  M.n = n;
+  M.d = d;
+  M.dpad = pad_dim(d);
+  M.npad = pad_rows(n);
+  M.kernel = kernel;
+  M.tail = tail;
+  M.ntail = (tail == B200RBF_TAIL_LINEAR) ? d + 1 : 1;
+  B2_TRY(M.centers.reserve((size_t)M.npad * M.dpad * sizeof(double)));
+  B2_TRY(M.coef.reserve((size_t)M.npad * sizeof(double)));
+  B2_TRY(M.tailc.reserve((size_t)M.ntail * sizeof(double)));
+  const long long tot = (long long)M.npad * M.dpad;
+  pad_points_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(Xu_dev, n, d, M.centers.as<double>(), M.npad,
+                                                                          M.dpad);
+  h->launches++;
+  B2_CUDA(cudaGetLastError());
+  const int cnt = M.npad > M.ntail ? M.npad : M.ntail;
+  split_coef_kernel<<<(cnt + 255) / 256, 256, 0, h->stream>>>(c_dev, M.ntail, n, M.coef.as<double>(), M.npad,
+                                                              M.tailc.as<double>());
+  h->launches++;
+  B2_CUDA(cudaGetLastError());
+  M.loaded = true;
+  h->score.valid = false;
+  return 0;
+}
+
+// lb / (ub - lb) -> device, padded to dpad (range pad = 1 so padded coordinates map to 0 / 1 = 0)
+int upload_box(b200rbf_ctx* h, const double* lb, const double* ub, int d, int dpad, DevBuf& box, bool* isotropic,
+               double* scale) {
+  B2_TRY(h->pin_small.reserve(4096 * sizeof(double)));
+  B2_CHECK(2 * dpad <= 4096, B200RBF_EINVAL, "dimension too large");
+  // the pinned scratch may still be in flight from the previous call on this stream
+  B2_CUDA(cudaStreamSynchronize(h->stream));
+  double* hb = reinterpret_cast<double*>(h->pin_small.p);
+  bool iso = true;
+  for (int k = 0; k < dpad; ++k) {
+    hb[k] = k < d ? lb[k] : 0.0;
+    hb[dpad + k] = k < d ? ub[k] - lb[k] : 1.0;  // utils.py:33 denominator
+    if (k < d && hb[dpad + k] != hb[dpad]) iso = false;
+  }
+  B2_TRY(box.reserve(2 * (size_t)dpad * sizeof(double)));
+  B2_CUDA(cudaMemcpyAsync(box.p, hb, 2 * (size_t)dpad * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (isotropic) *isotropic = iso;
+  if (scale) *scale = hb[dpad];
+  return 0;
+}
+
+struct ScorePlan {
+  bool with_phi = true;       // surrogate values
+  bool shared_min = false;    // min distance to the centers derived from the unit-box distance (x dscale)
+  double dscale = 1.0;
+  const double* dist_pts = nullptr;  // padded original-space points for the distance-only pass (nullptr: none)
+  int dist_npad = 0;
+  int dist_mode = 0;          // min_mode of the distance-only pass (1 write, 2 combine)
+};
+
+int launch_score_any(b200rbf_ctx* h, const ScoreArgs& a, int dpad, int kernel, bool exact, bool with_phi) {
+  switch ((dpad - 2) / 8) {
+    case 0: return launch_score_group0(h, a, dpad, kernel, exact, with_phi);
+    case 1: return launch_score_group1(h, a, dpad, kernel, exact, with_phi);
+    case 2: return launch_score_group2(h, a, dpad, kernel, exact, with_phi);
+    case 3: return launch_score_group3(h, a, dpad, kernel, exact, with_phi);
+    case 4: return launch_score_group4(h, a, dpad, kernel, exact, with_phi);
+    case 5: return launch_score_group5(h, a, dpad, kernel, exact, with_phi);
+    case 6: return launch_score_group6(h, a, dpad, kernel, exact, with_phi);
+    case 7: return launch_score_group7(h, a, dpad, kernel, exact, with_phi);
+  }
+  set_error("dim (padded %d) > %d is not supported by this build", dpad, kMaxRegDim);
+  return B200RBF_EINVAL;
+}
+
+// run the fused kernels over rows [r0, r0 + rows) of the device-resident candidates
+int score_rows(b200rbf_ctx* h, const ScorePlan& plan, const double* cand_dev, long long r0, long long rows,
+               const double* box, double* fvals, double* dmerit, double* parts, int nparts, int part_off) {
+  const Model& M = h->model;
+  ScoreArgs a;
+  memset(&a, 0, sizeof(a));
+  a.cand = cand_dev + r0 * M.d;
+  a.m = rows;
+  a.d = M.d;
+  a.parts = parts;
+  a.nparts = nparts;
+  a.part_off = part_off;
+  if (plan.with_phi) {
+    a.lb = box;
+    a.range = box + M.dpad;
+    a.pts = M.centers.as<double>();
+    a.coef = M.coef.as<double>();
+    a.tailc = M.tailc.as<double>();
+    a.npad = M.npad;
+    a.tail = M.tail;
+    a.dscale = plan.dscale;
+    a.min_mode = plan.shared_min ? 1 : 0;
+    a.fvals = fvals + r0;
+    a.dmerit = dmerit ? dmerit + r0 : nullptr;
+    B2_TRY(launch_score_any(h, a, M.dpad, M.kernel, h->exact_dist, true));
+  }
+  if (plan.dist_pts != nullptr) {
+    a.lb = nullptr;
+    a.range = nullptr;
+    a.pts = plan.dist_pts;
+    a.coef = nullptr;
+    a.tailc = nullptr;
+    a.npad = plan.dist_npad;
+    a.dscale = 1.0;
+    a.min_mode = plan.dist_mode;
+    a.fvals = nullptr;
+    a.dmerit = dmerit + r0;
+    B2_TRY(launch_score_any(h, a, M.dpad, 0, h->exact_dist, false));
+  }
+  return 0;
+}
+
+// stream `m` candidate rows (host or device) through score_rows; host rows are staged chunk by chunk so the
+// H2D copy of chunk i+1 overlaps the kernels of chunk i.  dst_dev receives the rows when they come from the host.
+int score_pipeline(b200rbf_ctx* h, const ScorePlan& plan, const double* cand, long long m, double* dst_dev,
+                   const double* box, double* fvals, double* dmerit, double* parts, int nparts,
+                   const double** cand_dev_out) {
+  const Model& M = h->model;
+  const PtrKind kind = ptr_kind(cand);
+  if (kind == kDevice) {
+    const long long kMaxRows = (long long)kScoreThreads * 0x7fff0000LL;
+    B2_CHECK(m <= kMaxRows, B200RBF_EINVAL, "too many candidates");
+    B2_TRY(score_rows(h, plan, cand, 0, m, box, fvals, dmerit, parts, nparts, 0));
+    *cand_dev_out = cand;
+    return 0;
+  }
+  const long long chunk = h->chunk_rows;
+  const size_t row_bytes = (size_t)M.d * sizeof(double);
+  if (kind == kPageable) {
+    const long long cr = m < chunk ? m : chunk;
+    B2_TRY(h->stage[0].reserve((size_t)cr * row_bytes));
+    if (m > chunk) B2_TRY(h->stage[1].reserve((size_t)cr * row_bytes));
+  }
+  int part_off = 0, slot = 0;
+  bool used[2] = {false, false};
+  for (long long r0 = 0; r0 < m; r0 += chunk, slot ^= 1) {
+    const long long rows = (m - r0 < chunk) ? (m - r0) : chunk;
+    const void* src = cand + r0 * M.d;
+    if (kind == kPageable) {
+      if (used[slot]) B2_CUDA(cudaEventSynchronize(h->ev_copy[slot]));  // staging buffer free again
+      memcpy(h->stage[slot].p, src, (size_t)rows * row_bytes);
+      src = h->stage[slot].p;
+    }
+    B2_CUDA(cudaMemcpyAsync(dst_dev + r0 * M.d, src, (size_t)rows * row_bytes, cudaMemcpyHostToDevice,
+                            h->copy_stream));
+    B2_CUDA(cudaEventRecord(h->ev_copy[slot], h->copy_stream));
+    used[slot] = true;
+    B2_CUDA(cudaStreamWaitEvent(h->stream, h->ev_copy[slot], 0));
+    B2_TRY(score_rows(h, plan, dst_dev, r0, rows, box, fvals, dmerit, parts, nparts, part_off));
+    part_off += (int)((rows + kScoreThreads - 1) / kScoreThreads);
+  }
+  *cand_dev_out = dst_dev;
+  return 0;
+}
+
+int count_parts(long long m, long long chunk, bool chunked) {
+  if (!chunked) return (int)((m + kScoreThreads - 1) / kScoreThreads);
+  long long total = 0;
+  for (long long r0 = 0; r0 < m; r0 += chunk) {
+    const long long rows = (m - r0 < chunk) ? (m - r0) : chunk;
+    total += (rows + kScoreThreads - 1) / kScoreThreads;
+  }
+  return (int)total;
+}
+
+}  // namespace
+}  // namespace b200rbf
+
+using namespace b200rbf;
+
+extern "C" {
+
+const char* b200rbf_last_error(void) { return g_err; }
+int b200rbf_version(void) { return 100; }
+
+int b200rbf_create(int device, b200rbf_handle* out) {
+  B2_CHECK(out != nullptr, B200RBF_EINVAL, "out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    set_error("no CUDA device available (%s); libb200rbf has no CPU fallback", cudaGetErrorString(e));
+    cudaGetLastError();
+    return B200RBF_ECUDA;
+  }
+  B2_CHECK(device >= 0 && device < count, B200RBF_EINVAL, "device %d out of range (%d devices)", device, count);
+  B2_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  B2_CUDA(cudaGetDeviceProperties(&prop, device));
+  B2_CHECK(prop.major == 10, B200RBF_ECUDA, "libb200rbf is built for sm_100a only; device %d is sm_%d%d", device,
+           prop.major, prop.minor);
+  b200rbf_ctx* h = new (std::nothrow) b200rbf_ctx();
+  B2_CHECK(h != nullptr, B200RBF_ENOMEM, "out of host memory");
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  B2_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  B2_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  h->stream = h->own_stream;
+  for (int i = 0; i < 2; ++i) B2_CUDA(cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming));
+  B2_CUDA(cudaEventCreate(&h->ev_t0));
+  B2_CUDA(cudaEventCreate(&h->ev_t1));
+  B2_CUDA(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
+  *out = h;
+  return 0;
+}
+
+int b200rbf_destroy(b200rbf_handle h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  cudaStreamSynchronize(h->copy_stream);
+  Model& M = h->model;
+  M.centers.release(); M.centersT.release(); M.coef.release(); M.tailc.release();
+  ScoreState& S = h->score;
+  S.cand_own.release(); S.fvals.release(); S.dmerit.release(); S.parts.release(); S.pair_parts.release();
+  S.stats.release(); S.winner.release(); S.results.release(); S.dist.release(); S.box.release();
+  FitState& F = h->fit;
+  F.A.release(); F.piv.release(); F.rhs.release(); F.work.release(); F.flags.release();
+  h->tmp_in.release(); h->tmp_out.release(); h->tmp_box.release();
+  h->stage[0].release(); h->stage[1].release(); h->pin_small.release();
+  for (int i = 0; i < 2; ++i) cudaEventDestroy(h->ev_copy[i]);
+  cudaEventDestroy(h->ev_t0); cudaEventDestroy(h->ev_t1); cudaEventDestroy(h->ev_done);
+  cudaStreamDestroy(h->own_stream);
+  cudaStreamDestroy(h->copy_stream);
+  delete h;
+  return 0;
+}
+
+int b200rbf_set_stream(b200rbf_handle h, void* s) {
+  B2_CHECK(h != nullptr, B200RBF_EINVAL, "handle is NULL");
+  h->stream = s ? reinterpret_cast<cudaStream_t>(s) : h->own_stream;
+  return 0;
+}
+
+int b200rbf_set_option(b200rbf_handle h, int option, long long value) {
+  B2_CHECK(h != nullptr, B200RBF_EINVAL, "handle is NULL");
+  switch (option) {
+    case B200RBF_OPT_EXACT_DIST: h->exact_dist = value != 0; return 0;
+    case B200RBF_OPT_CHUNK_ROWS:
+      B2_CHECK(value >= 256, B200RBF_EINVAL, "chunk rows must be >= 256");
+      h->chunk_rows = value;
+      return 0;
+    case B200RBF_OPT_LU_PANEL:
+      B2_CHECK(value >= 32 && value <= 128 && value % 32 == 0, B200RBF_EINVAL, "LU panel must be 32, 64, 96 or 128");
+      h->lu_panel = (int)value;
+      return 0;
+  }
+  set_error("unknown option %d", option);
+  return B200RBF_EINVAL;
+}
+
+long long b200rbf_launch_count(b200rbf_handle h) { return h ? h->launches : 0; }
+
+int b200rbf_load(b200rbf_handle h, const double* Xu, const double* c, int n, int d, int kernel, int tail) {
+  B2_CHECK(h && Xu && c, B200RBF_EINVAL, "NULL argument");
+  B2_TRY(check_model_args(n, d, kernel, tail));
+  B2_CUDA(cudaSetDevice(h->device));
+  const int t = (tail == B200RBF_TAIL_LINEAR) ? d + 1 : 1;
+  B2_TRY(h->tmp_in.reserve(((size_t)n * d + n + t) * sizeof(double)));
+  double* Xd = h->tmp_in.as<double>();
+  double* cd = Xd + (size_t)n * d;
+  B2_TRY(copy_in(h, Xd, Xu, (size_t)n * d * sizeof(double)));
+  B2_TRY(copy_in(h, cd, c, (size_t)(n + t) * sizeof(double)));
+  B2_TRY(install_model(h, Xd, cd, n, d, kernel, tail));
+  B2_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int b200rbf_fit(b200rbf_handle h, const double* Xu, const double* rhs, int n, int d, int kernel, int tail, double eta,
+                double* c_out, double* fit_seconds) {
+  B2_CHECK(h && Xu && rhs, B200RBF_EINVAL, "NULL argument");
+  B2_TRY(check_model_args(n, d, kernel, tail));
+  const int t = (tail == B200RBF_TAIL_LINEAR) ? d + 1 : 1;
+  B2_CHECK(n >= t, B200RBF_EINVAL, "need at least ntail = %d points to fit, have %d (rbf.py:111)", t, n);
+  B2_CUDA(cudaSetDevice(h->device));
+  const int N = n + t;
+  B2_TRY(h->tmp_in.reserve(((size_t)n * d + n + N) * sizeof(double)));
+  double* Xd = h->tmp_in.as<double>();
+  double* rd = Xd + (size_t)n * d;
+  double* cd = rd + n;
+  B2_TRY(h->pin_small.reserve(4096 * sizeof(double)));
+  B2_CUDA(cudaStreamSynchronize(h->stream));
+  int* info_host = reinterpret_cast<int*>(h->pin_small.p);
+  *info_host = 0;
+  B2_TRY(copy_in(h, Xd, Xu, (size_t)n * d * sizeof(double)));
+  B2_TRY(copy_in(h, rd, rhs, (size_t)n * sizeof(double)));
+  B2_CUDA(cudaEventRecord(h->ev_t0, h->stream));
+  B2_TRY(run_fit(h, Xd, rd, n, d, kernel, tail, eta, cd, info_host));
+  B2_TRY(install_model(h, Xd, cd, n, d, kernel, tail));
+  B2_CUDA(cudaEventRecord(h->ev_t1, h->stream));
+  if (c_out) B2_TRY(copy_out(h, c_out, cd, (size_t)N * sizeof(double)));
+  B2_CUDA(cudaStreamSynchronize(h->stream));
+  if (fit_seconds) {
+    float ms = 0.f;
+    B2_CUDA(cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1));
+    *fit_seconds = ms * 1e-3;
+  }
+  if (*info_host != 0) {
+    h->model.loaded = false;
+    set_error("singular matrix: exactly zero pivot at diagonal %d of the saddle-point system", *info_host);
+    return B200RBF_ESINGULAR;
+  }
+  return 0;
+}
+
+int b200rbf_predict(b200rbf_handle h, const double* x, long long m, const double* lb, const double* ub, double* out) {
+  B2_CHECK(h && x && lb && ub && out, B200RBF_EINVAL, "NULL argument");
+  B2_CHECK(h->model.loaded, B200RBF_ESTATE, "no model resident: call b200rbf_fit or b200rbf_load first");
+  B2_CHECK(m >= 0, B200RBF_EINVAL, "negative row count");
+  if (m == 0) return 0;
+  B2_CUDA(cudaSetDevice(h->device));
+  const Model& M = h->model;
+  B2_TRY(upload_box(h, lb, ub, M.d, M.dpad, h->tmp_box, nullptr, nullptr));
+  const bool host_in = ptr_kind(x) != kDevice, host_out = ptr_kind(out) != kDevice;
+  const int nparts = count_parts(m, h->chunk_rows, host_in);
+  size_t need = (size_t)4 * nparts * sizeof(double) + 64;
+  const size_t off_f = need;
+  if (host_out) need += (size_t)m * sizeof(double);
+  B2_TRY(h->tmp_out.reserve(need));
+  double* parts = h->tmp_out.as<double>();
+  double* fv = host_out ? reinterpret_cast<double*>(reinterpret_cast<char*>(h->tmp_out.p) + off_f) : out;
+  double* xdev = nullptr;
+  if (host_in) {
+    B2_TRY(h->tmp_in.reserve((size_t)m * M.d * sizeof(double)));
+    xdev = h->tmp_in.as<double>();
+  }
+  ScorePlan plan;
+  const double* used = nullptr;
+  B2_TRY(score_pipeline(h, plan, x, m, xdev, h->tmp_box.as<double>(), fv, nullptr, parts, nparts, &used));
+  if (host_out) B2_TRY(copy_out(h, out, fv, (size_t)m * sizeof(double)));
+  B2_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int b200rbf_predict_deriv(b200rbf_handle h, const double* x, long long m, const double* lb, const double* ub,
+                          double* out) {
+  B2_CHECK(h && x && lb && ub && out, B200RBF_EINVAL, "NULL argument");
+  B2_CHECK(h->model.loaded, B200RBF_ESTATE, "no model resident: call b200rbf_fit or b200rbf_load first");
+  B2_CHECK(m >= 0, B200RBF_EINVAL, "negative row count");
+  if (m == 0) return 0;
+  B2_CUDA(cudaSetDevice(h->device));
+  const Model& M = h->model;
+  B2_TRY(upload_box(h, lb, ub, M.d, M.dpad, h->tmp_box, nullptr, nullptr));
+  const bool host_in = ptr_kind(x) != kDevice, host_out = ptr_kind(out) != kDevice;
+  const double* xdev = x;
+  if (host_in) {
+    B2_TRY(h->tmp_in.reserve((size_t)m * M.d * sizeof(double)));
+    B2_TRY(copy_in(h, h->tmp_in.p, x, (size_t)m * M.d * sizeof(double)));
+    xdev = h->tmp_in.as<double>();
+  }
+  size_t scratch = 0;
+  B2_TRY(deriv_scratch_doubles(h, m, &scratch));
+  const size_t out_doubles = host_out ? (size_t)m * M.d : 0;
+  B2_TRY(h->tmp_out.reserve((scratch + out_doubles) * sizeof(double)));
+  double* sc = h->tmp_out.as<double>();
+  double* od = host_out ? sc + scratch : out;
+  B2_TRY(launch_deriv(h, xdev, m, h->tmp_box.as<double>(), h->tmp_box.as<double>() + M.dpad, od, sc));
+  if (host_out) B2_TRY(copy_out(h, out, od, (size_t)m * M.d * sizeof(double)));
+  B2_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int b200rbf_score(b200rbf_handle h, const double* cand, long long m, const double* lb, const double* ub,
+                  const double* Xdist, int ndist, int alias_centers, double* fvals_out, double* dmerit_out,
+                  double* stats_out) {
+  B2_CHECK(h && cand && lb && ub && Xdist, B200RBF_EINVAL, "NULL argument");
+  B2_CHECK(h->model.loaded, B200RBF_ESTATE, "no model resident: call b200rbf_fit or b200rbf_load first");
+  B2_CHECK(m >= 1, B200RBF_EINVAL, "need at least one candidate");
+  B2_CHECK(ndist >= 1, B200RBF_EINVAL, "need at least one evaluated or pending point");
+  B2_CUDA(cudaSetDevice(h->device));
+  const Model& M = h->model;
+  ScoreState& S = h->score;
+  S.valid = false;
+  B2_CHECK(!alias_centers || ndist >= M.n, B200RBF_EINVAL, "alias_centers needs ndist >= n");
+  bool iso = false;
+  double scale = 1.0;
+  B2_TRY(upload_box(h, lb, ub, M.d, M.dpad, S.box, &iso, &scale));
+
+  ScorePlan plan;
+  plan.shared_min = alias_centers && iso;
+  plan.dscale = plan.shared_min ? scale : 1.0;
+  const int first = plan.shared_min ? M.n : 0;  // rows of Xdist that still need the original-space pass
+  const int extra = ndist - first;
+  if (extra > 0) {
+    const int npd = pad_rows(extra);
+    B2_TRY(S.dist.reserve(((size_t)npd * M.dpad + (size_t)extra * M.d) * sizeof(double)));
+    double* padded = S.dist.as<double>();
+    double* raw = padded + (size_t)npd * M.dpad;
+    B2_TRY(copy_in(h, raw, Xdist + (size_t)first * M.d, (size_t)extra * M.d * sizeof(double)));
+    const long long tot = (long long)npd * M.dpad;
+    pad_points_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(raw, extra, M.d, padded, npd, M.dpad);
+    h->launches++;
+    B2_CUDA(cudaGetLastError());
+    plan.dist_pts = padded;
+    plan.dist_npad = npd;
+    plan.dist_mode = plan.shared_min ? 2 : 1;
+  }
+
+  const bool host_in = ptr_kind(cand) != kDevice;
+  const int nparts = count_parts(m, h->chunk_rows, host_in);
+  S.nparts = nparts > h->sm_count * 8 ? nparts : h->sm_count * 8;  // also holds the update kernel's partials
+  B2_TRY(S.parts.reserve((size_t)4 * S.nparts * sizeof(double)));
+  B2_TRY(S.fvals.reserve((size_t)m * sizeof(double)));
+  B2_TRY(S.dmerit.reserve((size_t)m * sizeof(double)));
+  B2_TRY(S.stats.reserve(64));
+  B2_TRY(S.winner.reserve((size_t)M.dpad * sizeof(double)));
+  B2_TRY(S.pair_parts.reserve((size_t)(h->sm_count * 8 + 8) * 16));
+  double* own = nullptr;
+  if (host_in) {
+    B2_TRY(S.cand_own.reserve((size_t)m * M.d * sizeof(double)));
+    own = S.cand_own.as<double>();
+  }
+  B2_TRY(score_pipeline(h, plan, cand, m, own, S.box.as<double>(), S.fvals.as<double>(), S.dmerit.as<double>(),
+                        S.parts.as<double>(), S.nparts, &S.cand));
+  B2_TRY(launch_stats(h, S.parts.as<double>(), S.nparts, nparts, 3, S.stats.as<double>()));
+  S.m = m;
+  S.d = M.d;
+  if (fvals_out) B2_TRY(copy_out(h, fvals_out, S.fvals.p, (size_t)m * sizeof(double)));
+  if (dmerit_out) B2_TRY(copy_out(h, dmerit_out, S.dmerit.p, (size_t)m * sizeof(double)));
+  if (stats_out) B2_TRY(copy_out(h, stats_out, S.stats.p, 4 * sizeof(double)));
+  B2_CUDA(cudaStreamSynchronize(h->stream));
+  S.valid = true;
+  return 0;
+}
+
+int b200rbf_select(b200rbf_handle h, const double* weights, int p, double dtol, long long* idx_out,
+                   double* merit_out) {
+  B2_CHECK(h && weights && idx_out, B200RBF_EINVAL, "NULL argument");
+  B2_CHECK(h->score.valid, B200RBF_ESTATE, "nothing scored: call b200rbf_score first");
+  B2_CHECK(p >= 1, B200RBF_EINVAL, "num_pts must be >= 1");
+  B2_CUDA(cudaSetDevice(h->device));
+  ScoreState& S = h->score;
+  const Model& M = h->model;
+  B2_TRY(S.results.reserve((size_t)p * 16));
+  B2_TRY(h->pin_small.reserve(((size_t)p * 16 > 4096 * 8) ? (size_t)p * 16 : 4096 * 8));
+  char* res = reinterpret_cast<char*>(S.results.p);
+  for (int i = 0; i < p; ++i) {
+    int nb = 0;
+    B2_TRY(launch_merit_argmin(h, S.fvals.as<double>(), S.dmerit.as<double>(), S.m, S.stats.as<double>(), 0,
+                               weights[i], dtol, 0, S.pair_parts.p, &nb));
+    B2_TRY(launch_pick(h, S.pair_parts.p, nb, S.cand, S.d, S.fvals.as<double>(), S.winner.as<double>(), M.dpad,
+                       res + (size_t)i * 16, nullptr));
+    if (i + 1 < p) {
+      int cnt = 0;
+      B2_TRY(launch_update(h, S.cand, S.m, S.d, S.winner.as<double>(), S.dmerit.as<double>(), S.parts.as<double>(),
+                           S.nparts, &cnt, h->exact_dist));
+      B2_TRY(launch_stats(h, S.parts.as<double>(), S.nparts, cnt, 2, S.stats.as<double>()));
+    }
+  }
+  B2_CUDA(cudaMemcpyAsync(h->pin_small.p, res, (size_t)p * 16, cudaMemcpyDeviceToHost, h->stream));
+  B2_CUDA(cudaStreamSynchronize(h->stream));
+  const char* hp = reinterpret_cast<const char*>(h->pin_small.p);
+  for (int i = 0; i < p; ++i) {
+    double v;
+    long long ix;
+    memcpy(&v, hp + (size_t)i * 16, 8);
+    memcpy(&ix, hp + (size_t)i * 16 + 8, 8);
+    idx_out[i] = ix;
+    if (merit_out) merit_out[i] = v;
+  }
+  // the resident scores were consumed (fvals poisoned, dmerit updated): a second select needs a new score
+  S.valid = false;
+  return 0;
+}
+
+int b200rbf_shard_stats(b200rbf_handle h, double* stats_dev) {
+  B2_CHECK(h && stats_dev, B200RBF_EINVAL, "NULL argument");
+  B2_CHECK(h->score.valid, B200RBF_ESTATE, "nothing scored: call b200rbf_score first");
+  B2_CUDA(cudaSetDevice(h->device));
+  negate_stats_kernel<<<1, 32, 0, h->stream>>>(h->score.stats.as<double>(), stats_dev);
+  h->launches++;
+  B2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int b200rbf_shard_argmin(b200rbf_handle h, double w, double dtol, const double* stats_dev, long long idx_offset,
+                         void* pair_dev) {
+  B2_CHECK(h && stats_dev && pair_dev, B200RBF_EINVAL, "NULL argument");
+  B2_CHECK(h->score.valid, B200RBF_ESTATE, "nothing scored: call b200rbf_score first");
+  B2_CUDA(cudaSetDevice(h->device));
+  ScoreState& S = h->score;
+  int nb = 0;
+  B2_TRY(launch_merit_argmin(h, S.fvals.as<double>(), S.dmerit.as<double>(), S.m, stats_dev, 1, w, dtol, idx_offset,
+                             S.pair_parts.p, &nb));
+  B2_TRY(launch_pick(h, S.pair_parts.p, nb, nullptr, 0, nullptr, nullptr, 0, nullptr, pair_dev));
+  return 0;
+}
+
+int b200rbf_shard_take(b200rbf_handle h, long long local_idx, double* winner_dev) {
+  B2_CHECK(h && winner_dev, B200RBF_EINVAL, "NULL argument");
+  B2_CHECK(h->score.valid, B200RBF_ESTATE, "nothing scored: call b200rbf_score first");
+  ScoreState& S = h->score;
+  B2_CHECK(local_idx >= 0 && local_idx < S.m, B200RBF_EINVAL, "row %lld out of range", local_idx);
+  B2_CUDA(cudaSetDevice(h->device));
+  B2_TRY(launch_take(h, S.cand, S.d, local_idx, S.fvals.as<double>(), winner_dev, S.d));
+  return 0;
+}
+
+int b200rbf_shard_update(b200rbf_handle h, const double* winner_dev) {
+  B2_CHECK(h && winner_dev, B200RBF_EINVAL, "NULL argument");
+  B2_CHECK(h->score.valid, B200RBF_ESTATE, "nothing scored: call b200rbf_score first");
+  B2_CUDA(cudaSetDevice(h->device));
+  ScoreState& S = h->score;
+  int cnt = 0;
+  B2_TRY(launch_update(h, S.cand, S.m, S.d, winner_dev, S.dmerit.as<double>(), S.parts.as<double>(), S.nparts, &cnt,
+                       h->exact_dist));
+  B2_TRY(launch_stats(h, S.parts.as<double>(), S.nparts, cnt, 2, S.stats.as<double>()));
+  return 0;
+}
+
+int b200rbf_fp64_peaks(b200rbf_handle h, double ms, double* out) {
+  B2_CHECK(h && out, B200RBF_EINVAL, "NULL argument");
+  B2_CUDA(cudaSetDevice(h->device));
+  return run_fp64_peaks(h, ms, out);
+}
+
+/* ---- test hooks (not part of the drop-in surface; used by tests/ to localise failures) ---- */
+int b200rbf_dbg_lu(b200rbf_handle h, double* A_host, int N, int nrhs, int* ipiv_host, int* info) {
+  // A_host: N x (N + nrhs) row-major; factored in place, right-hand sides replaced by L^-1 P b
+  B2_CHECK(h && A_host && ipiv_host && info, B200RBF_EINVAL, "NULL argument");
+  B2_CUDA(cudaSetDevice(h->device));
+  const int rcol0 = (N + 1) & ~1, ncols = rcol0 + nrhs, ld = (ncols + 7) & ~7;
+  DevBuf A, piv;
+  B2_TRY(A.reserve(((size_t)N * ld + 1024) * sizeof(double)));
+  B2_TRY(piv.reserve(((size_t)N + 16) * sizeof(int)));
+  B2_CUDA(cudaMemsetAsync(A.p, 0, (size_t)N * ld * sizeof(double), h->stream));
+  B2_CUDA(cudaMemsetAsync(piv.p, 0, ((size_t)N + 16) * sizeof(int), h->stream));
+  B2_CUDA(cudaMemcpy2DAsync(A.p, (size_t)ld * 8, A_host, (size_t)(N + nrhs) * 8, (size_t)N * 8, N,
+                            cudaMemcpyHostToDevice, h->stream));
+  if (nrhs > 0)
+    B2_CUDA(cudaMemcpy2DAsync(A.as<double>() + rcol0, (size_t)ld * 8, A_host + N, (size_t)(N + nrhs) * 8,
+                              (size_t)nrhs * 8, N, cudaMemcpyHostToDevice, h->stream));
+  int rc = run_lu_debug(h, A.as<double>(), ld, N, rcol0, ncols, piv.as<int>(), piv.as<int>() + N);
+  if (rc == 0) {
+    cudaMemcpy2DAsync(A_host, (size_t)(N + nrhs) * 8, A.p, (size_t)ld * 8, (size_t)N * 8, N, cudaMemcpyDeviceToHost,
+                      h->stream);
+    if (nrhs > 0)
+      cudaMemcpy2DAsync(A_host + N, (size_t)(N + nrhs) * 8, A.as<double>() + rcol0, (size_t)ld * 8, (size_t)nrhs * 8, N,
+                        cudaMemcpyDeviceToHost, h->stream);
+    cudaMemcpyAsync(ipiv_host, piv.p, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    cudaMemcpyAsync(info, piv.as<int>() + N, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+  }
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  A.release();
+  piv.release();
+  if (rc != 0) return rc;
+  B2_CUDA(e);
+  return 0;
+}
+
+int b200rbf_dbg_gemm(b200rbf_handle h, double* C_host, const double* A_host, const double* B_host, int M, int Nc,
+                     int K, double* seconds) {
+  // C (M x Nc) -= A (M x K) * B (K x Nc), row-major host arrays; K % 16 == 0, Nc even
+  B2_CHECK(h && C_host && A_host && B_host, B200RBF_EINVAL, "NULL argument");
+  B2_CHECK(K % 16 == 0 && K > 0, B200RBF_EINVAL, "K must be a positive multiple of 16");
+  B2_CUDA(cudaSetDevice(h->device));
+  const int ldc = (Nc + 1) & ~1, lda = K, ldb = ldc;
+  DevBuf C, A, B;
+  B2_TRY(C.reserve(((size_t)M * ldc + 256) * 8));
+  B2_TRY(A.reserve(((size_t)M * lda + 256) * 8));
+  B2_TRY(B.reserve(((size_t)K * ldb + 256) * 8));
+  B2_CUDA(cudaMemsetAsync(B.p, 0, ((size_t)K * ldb + 256) * 8, h->stream));
+  B2_CUDA(cudaMemcpy2DAsync(C.p, (size_t)ldc * 8, C_host, (size_t)Nc * 8, (size_t)Nc * 8, M, cudaMemcpyHostToDevice,
+                            h->stream));
+  B2_CUDA(cudaMemcpyAsync(A.p, A_host, (size_t)M * K * 8, cudaMemcpyHostToDevice, h->stream));
+  B2_CUDA(cudaMemcpy2DAsync(B.p, (size_t)ldb * 8, B_host, (size_t)Nc * 8, (size_t)Nc * 8, K, cudaMemcpyHostToDevice,
+                            h->stream));
+  B2_CUDA(cudaEventRecord(h->ev_t0, h->stream));
+  int rc = run_gemm_debug(h, C.as<double>(), ldc, A.as<double>(), lda, B.as<double>(), ldb, M, Nc, K);
+  cudaEventRecord(h->ev_t1, h->stream);
+  if (rc == 0)
+    cudaMemcpy2DAsync(C_host, (size_t)Nc * 8, C.p, (size_t)ldc * 8, (size_t)Nc * 8, M, cudaMemcpyDeviceToHost,
+                      h->stream);
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  if (seconds) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1);
+    *seconds = ms * 1e-3;
+  }
+  C.release();
+  A.release();
+  B.release();
+  if (rc != 0) return rc;
+  B2_CUDA(e);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,198 @@
+// Shared declarations for libb200rbf.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/b200rbf.h"
+
+namespace b200rbf {
+
+// ---------------------------------------------------------------- errors
+void set_error(const char* fmt, ...);
+#define B2_CUDA(expr)                                                                             \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      b200rbf::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return B200RBF_ECUDA;                                                                       \
+    }                                                                                             \
+  } while (0)
+#define B2_TRY(expr)          \
+  do {                        \
+    int _r = (expr);          \
+    if (_r != 0) return _r;   \
+  } while (0)
+#define B2_CHECK(cond, code, ...)        \
+  do {                                   \
+    if (!(cond)) {                       \
+      b200rbf::set_error(__VA_ARGS__);   \
+      return (code);                     \
+    }                                    \
+  } while (0)
+
+// ---------------------------------------------------------------- device buffers (grow-only)
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      e = cudaMalloc(&p, bytes);
+      want = bytes;
+    }
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+      p = nullptr;
+      return B200RBF_ENOMEM;
+    }
+    cap = want;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMallocHost(&p, bytes);
+    if (e != cudaSuccess) {
+      set_error("cudaMallocHost(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+      p = nullptr;
+      return B200RBF_ENOMEM;
+    }
+    cap = bytes;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+// ---------------------------------------------------------------- constants
+constexpr int kMaxRegDim = 64;     // candidate coordinates held in registers up to this (padded) dimension
+constexpr int kScoreThreads = 256; // threads (= candidates) per CTA in the score kernels
+constexpr int kTileRows = 32;      // center rows per shared-memory tile (TMA bulk copy granule)
+constexpr int kStages = 3;         // tile ring depth
+constexpr int kJT = 4;             // centers processed together per thread (independent accumulators)
+constexpr int kMaxParts = 1 << 20; // upper bound on per-CTA partial slots
+
+inline int pad_dim(int d) { return (d + 1) & ~1; }                       // even: rows are multiples of 16 B
+inline int pad_rows(int n) { return ((n + kJT - 1) / kJT) * kJT; }       // multiples of kJT (duplicates of last row)
+
+// ---------------------------------------------------------------- the handle
+struct Model {
+  int n = 0, d = 0, dpad = 0, npad = 0, kernel = 0, tail = 0, ntail = 0;
+  bool loaded = false;
+  DevBuf centers;   // npad x dpad unit-box coordinates (pad rows = last row, pad dims = 0)
+  DevBuf centersT;  // dpad x npadT  transposed copy for predict_deriv
+  DevBuf coef;      // npad RBF weights (pad = 0)
+  DevBuf tailc;     // ntail tail coefficients (lambda_0, lambda_1..d)
+  int npadT = 0;
+};
+
+struct ScoreState {
+  long long m = 0;          // resident candidates
+  int d = 0;
+  bool valid = false;
+  const double* cand = nullptr;  // device pointer (own buffer or caller's)
+  DevBuf cand_own;
+  DevBuf fvals, dmerit;
+  DevBuf parts;             // 4 x nparts per-CTA partial stats
+  int nparts = 0;
+  DevBuf pair_parts;        // per-CTA (merit, index) partials
+  DevBuf stats;             // {fmin, fmax, dmin, dmax}
+  DevBuf winner;            // dpad doubles
+  DevBuf results;           // p x {int64 idx, double merit}
+  DevBuf dist;              // padded distance point set
+  DevBuf box;               // 2 x dpad : lb, (ub - lb)
+};
+
+struct FitState {
+  DevBuf A;      // N x ld saddle-point matrix, row-major, overwritten by L\U
+  DevBuf piv;    // N int pivot rows
+  DevBuf rhs;    // N
+  DevBuf work;   // cooperative panel scratch
+  DevBuf flags;
+};
+
+}  // namespace b200rbf
+
+struct b200rbf_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_t0 = nullptr, ev_t1 = nullptr, ev_done = nullptr;
+  b200rbf::PinBuf stage[2];
+  b200rbf::PinBuf pin_small;
+  long long launches = 0;
+  bool exact_dist = false;
+  long long chunk_rows = 65536;
+  int lu_panel = 128;
+  b200rbf::Model model;
+  b200rbf::ScoreState score;
+  b200rbf::FitState fit;
+  b200rbf::DevBuf tmp_in, tmp_out, tmp_box;
+};
+
+namespace b200rbf {
+
+// kernel launch entry points implemented in the .cu files -------------------------------------------
+struct ScoreArgs {
+  const double* cand;      // m x d (original coordinates), row-major, device
+  long long m;
+  int d;
+  const double* lb;        // dpad (device) or nullptr => candidates are used as-is (no unit-box map)
+  const double* range;     // dpad : ub - lb
+  const double* pts;       // npad x DPAD point set (unit-box centers, or original-space distance set)
+  const double* coef;      // npad weights (nullptr in distance-only mode)
+  const double* tailc;     // ntail
+  int npad;
+  int tail;                // B200RBF_TAIL_*
+  double dscale;           // distance-only / shared mode: factor from unit to original metric
+  int min_mode;            // 0: none, 1: write dmerit = dscale*sqrt(min r2), 2: dmerit = min(dmerit, that)
+  double* fvals;           // m (nullptr in distance-only mode)
+  double* dmerit;          // m
+  double* parts;           // 4 x nparts partial stats
+  int nparts;
+  int part_off;            // first partial slot of this launch
+};
+
+// parts: 4 rows {fmin, fmax, dmin, dmax} x `stride` slots, `count` of them valid; which: bit0 f rows, bit1 d rows
+int launch_stats(b200rbf_ctx* h, const double* parts, int stride, int count, int which, double* stats);
+int launch_merit_argmin(b200rbf_ctx* h, const double* fvals, const double* dmerit, long long m, const double* stats,
+                        int stats_negated, double w, double dtol, long long idx_off, void* pair_parts, int* nblocks);
+int launch_pick(b200rbf_ctx* h, const void* pair_parts, int nparts, const double* cand, int d, double* fvals,
+                double* winner, int dpad, void* result_slot, void* pair_out);
+int launch_take(b200rbf_ctx* h, const double* cand, int d, long long idx, double* fvals, double* winner, int dpad);
+int launch_update(b200rbf_ctx* h, const double* cand, long long m, int d, const double* winner, double* dmerit,
+                  double* parts, int stride, int* count_out, bool exact);
+int launch_deriv(b200rbf_ctx* h, const double* x, long long m, const double* lb, const double* range, double* out,
+                 double* scratch);
+int run_fit(b200rbf_ctx* h, const double* Xu_dev, const double* rhs_dev, int n, int d, int kernel, int tail,
+            double eta, double* c_dev, int* info);
+int run_fp64_peaks(b200rbf_ctx* h, double ms, double* out);
+
+}  // namespace b200rbf

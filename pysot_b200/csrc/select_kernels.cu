@@ -1,0 +1,294 @@
+// Selection half of weighted_distance_merit (candidate_srbf.py:43-55) on device-resident scores.
+//   stats_kernel        : x.min() / x.max() of utils.py:60-61 from per-CTA partials
+//   merit_argmin_kernel : merit = w*fhat + (1-w)*(1-dhat); merit[dmerit<dtol]=inf; first argmin   (:46-49)
+//   pick_kernel         : fvals[jj] = inf; winner = cand[jj]                                       (:50-51)
+//   update_kernel       : dmerit = minimum(dmerit, ||cand - winner||) + new min/max partials       (:54-55)
+// All of these are HBM-bound streaming passes over m (x d) doubles.
+#include "common.cuh"
+
+namespace b200rbf {
+
+namespace {
+
+constexpr int kSelThreads = 256;
+
+__device__ __forceinline__ double d_inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+
+// numpy argmin ordering: NaN beats everything (np.argmin returns the first NaN), then value, then lowest index
+__device__ __forceinline__ bool better(double av, long long ai, double bv, long long bi) {
+  const bool an = isnan(av), bn = isnan(bv);
+  if (an || bn) {
+    if (an && bn) return ai < bi;
+    return an;
+  }
+  if (av < bv) return true;
+  if (av > bv) return false;
+  return ai < bi;
+}
+
+struct Pair {
+  double v;
+  long long i;
+};
+
+__device__ __forceinline__ Pair warp_argmin(Pair p) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double ov = __shfl_xor_sync(0xffffffffu, p.v, o);
+    long long oi = __shfl_xor_sync(0xffffffffu, p.i, o);
+    if (better(ov, oi, p.v, p.i)) {
+      p.v = ov;
+      p.i = oi;
+    }
+  }
+  return p;
+}
+
+__device__ Pair block_argmin(Pair p, Pair* s_pairs) {
+  p = warp_argmin(p);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) s_pairs[warp] = p;
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = blockDim.x >> 5;
+    Pair q = lane < nw ? s_pairs[lane] : Pair{d_inf(), 0x7fffffffffffffffLL};
+    q = warp_argmin(q);
+    if (lane == 0) s_pairs[0] = q;
+  }
+  __syncthreads();
+  return s_pairs[0];
+}
+
+// which: bit0 -> reduce f rows (0,1), bit1 -> reduce d rows (2,3)
+__global__ void __launch_bounds__(1024) stats_kernel(const double* __restrict__ parts, int stride, int count,
+                                                     int which, double* __restrict__ stats) {
+  __shared__ double s[4][32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double v[4] = {d_inf(), -d_inf(), d_inf(), -d_inf()};
+  for (int i = tid; i < count; i += blockDim.x) {
+    if (which & 1) {
+      v[0] = fmin(v[0], parts[i]);
+      v[1] = fmax(v[1], parts[stride + i]);
+    }
+    if (which & 2) {
+      v[2] = fmin(v[2], parts[2 * stride + i]);
+      v[3] = fmax(v[3], parts[3 * stride + i]);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v[0] = fmin(v[0], __shfl_xor_sync(0xffffffffu, v[0], o));
+    v[1] = fmax(v[1], __shfl_xor_sync(0xffffffffu, v[1], o));
+    v[2] = fmin(v[2], __shfl_xor_sync(0xffffffffu, v[2], o));
+    v[3] = fmax(v[3], __shfl_xor_sync(0xffffffffu, v[3], o));
+  }
+  if (lane == 0)
+    for (int q = 0; q < 4; ++q) s[q][warp] = v[q];
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = blockDim.x >> 5;
+    double r[4];
+    r[0] = lane < nw ? s[0][lane] : d_inf();
+    r[1] = lane < nw ? s[1][lane] : -d_inf();
+    r[2] = lane < nw ? s[2][lane] : d_inf();
+    r[3] = lane < nw ? s[3][lane] : -d_inf();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      r[0] = fmin(r[0], __shfl_xor_sync(0xffffffffu, r[0], o));
+      r[1] = fmax(r[1], __shfl_xor_sync(0xffffffffu, r[1], o));
+      r[2] = fmin(r[2], __shfl_xor_sync(0xffffffffu, r[2], o));
+      r[3] = fmax(r[3], __shfl_xor_sync(0xffffffffu, r[3], o));
+    }
+    if (lane == 0) {
+      if (which & 1) {
+        stats[0] = r[0];
+        stats[1] = r[1];
+      }
+      if (which & 2) {
+        stats[2] = r[2];
+        stats[3] = r[3];
+      }
+    }
+  }
+}
+
+// stats: {fmin, fmax, dmin, dmax}, or {fmin, -fmax, dmin, -dmax} when negated != 0 (sharded path)
+__global__ void __launch_bounds__(kSelThreads) merit_argmin_kernel(const double* __restrict__ fvals,
+                                                                   const double* __restrict__ dmerit, long long m,
+                                                                   const double* __restrict__ stats, int negated,
+                                                                   double w, double dtol, long long idx_off,
+                                                                   Pair* __restrict__ out) {
+  __shared__ Pair s_pairs[kSelThreads / 32];
+  const double fmn = stats[0], fmx = negated ? -stats[1] : stats[1];
+  const double dmn = stats[2], dmx = negated ? -stats[3] : stats[3];
+  const bool fflat = (fmx == fmn), dflat = (dmx == dmn);  // utils.py:62-63 -> ones
+  const double frange = __dsub_rn(fmx, fmn), drange = __dsub_rn(dmx, dmn);
+  const double omw = __dsub_rn(1.0, w);
+  Pair best{d_inf(), 0x7fffffffffffffffLL};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
+    const double f = fvals[i], dd = dmerit[i];
+    // fvals is rescaled once and THEN poisoned with inf at picked rows (candidate_srbf.py:40,50)
+    double fh = isinf(f) ? f : (fflat ? 1.0 : __ddiv_rn(__dsub_rn(f, fmn), frange));
+    double dh = dflat ? 1.0 : __ddiv_rn(__dsub_rn(dd, dmn), drange);
+    double merit = __dadd_rn(__dmul_rn(w, fh), __dmul_rn(omw, __dsub_rn(1.0, dh)));
+    if (dd < dtol) merit = d_inf();
+    const long long gi = i + idx_off;
+    if (better(merit, gi, best.v, best.i)) {
+      best.v = merit;
+      best.i = gi;
+    }
+  }
+  best = block_argmin(best, s_pairs);
+  if (threadIdx.x == 0) out[blockIdx.x] = best;
+}
+
+// single CTA: reduce the per-CTA pairs; optionally apply the pick locally
+__global__ void __launch_bounds__(kSelThreads) pick_kernel(const Pair* __restrict__ parts, int nparts,
+                                                           const double* __restrict__ cand, int d,
+                                                           double* __restrict__ fvals, double* __restrict__ winner,
+                                                           int dpad, Pair* __restrict__ result_slot,
+                                                           Pair* __restrict__ pair_out) {
+  __shared__ Pair s_pairs[kSelThreads / 32];
+  Pair best{d_inf(), 0x7fffffffffffffffLL};
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) {
+    Pair p = parts[i];
+    if (better(p.v, p.i, best.v, best.i)) best = p;
+  }
+  best = block_argmin(best, s_pairs);
+  if (pair_out != nullptr && threadIdx.x == 0) *pair_out = best;
+  if (result_slot != nullptr) {
+    if (threadIdx.x == 0) {
+      *result_slot = best;
+      fvals[best.i] = d_inf();
+    }
+    for (int k = threadIdx.x; k < dpad; k += blockDim.x) winner[k] = k < d ? cand[best.i * (long long)d + k] : 0.0;
+  }
+}
+
+__global__ void take_kernel(const double* __restrict__ cand, int d, long long idx, double* __restrict__ fvals,
+                            double* __restrict__ winner, int dpad) {
+  if (threadIdx.x == 0) fvals[idx] = d_inf();
+  for (int k = threadIdx.x; k < dpad; k += blockDim.x) winner[k] = k < d ? cand[idx * (long long)d + k] : 0.0;
+}
+
+// rows are staged through shared memory with coalesced loads, then one thread walks one row sequentially
+// (same summation order as cdist, candidate_srbf.py:54)
+constexpr int kUpdRows = 128;
+
+template <bool EXACT>
+__global__ void __launch_bounds__(kUpdRows) update_kernel(const double* __restrict__ cand, long long m, int d,
+                                                          const double* __restrict__ winner,
+                                                          double* __restrict__ dmerit, double* __restrict__ parts,
+                                                          int nparts, int rpp /* rows per pass <= kUpdRows */) {
+  extern __shared__ double s_rows[];  // rpp x (d | 1) doubles, + d winner
+  const int ds = d | 1;               // odd stride: conflict-free column walks
+  double* s_win = s_rows + (size_t)rpp * ds;
+  __shared__ double s_red[2][kUpdRows / 32];
+  const int tid = threadIdx.x;
+  for (int k = tid; k < d; k += blockDim.x) s_win[k] = winner[k];
+  double dmn = d_inf(), dmx = -d_inf();
+  for (long long base = (long long)blockIdx.x * rpp; base < m; base += (long long)gridDim.x * rpp) {
+    const long long rows = min((long long)rpp, m - base);
+    const long long total = rows * d;
+    const double* src = cand + base * d;
+    __syncthreads();
+    for (long long e = tid; e < total; e += blockDim.x) {
+      const int r = (int)(e / d), k = (int)(e - (long long)r * d);
+      s_rows[r * ds + k] = src[e];
+    }
+    __syncthreads();
+    if (tid < rows) {
+      const double* rp = s_rows + tid * ds;
+      double acc = 0.0;
+      for (int k = 0; k < d; ++k) {
+        const double t = rp[k] - s_win[k];
+        acc = EXACT ? __dadd_rn(acc, __dmul_rn(t, t)) : fma(t, t, acc);
+      }
+      const double nd = fmin(dmerit[base + tid], sqrt(acc));
+      dmerit[base + tid] = nd;
+      dmn = fmin(dmn, nd);
+      dmx = fmax(dmx, nd);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    dmn = fmin(dmn, __shfl_xor_sync(0xffffffffu, dmn, o));
+    dmx = fmax(dmx, __shfl_xor_sync(0xffffffffu, dmx, o));
+  }
+  if ((tid & 31) == 0) {
+    s_red[0][tid >> 5] = dmn;
+    s_red[1][tid >> 5] = dmx;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < kUpdRows / 32; ++w) {
+      dmn = fmin(dmn, s_red[0][w]);
+      dmx = fmax(dmx, s_red[1][w]);
+    }
+    parts[2 * nparts + blockIdx.x] = dmn;
+    parts[3 * nparts + blockIdx.x] = dmx;
+  }
+}
+
+}  // namespace
+
+int launch_stats(b200rbf_ctx* h, const double* parts, int stride, int count, int which, double* stats) {
+  stats_kernel<<<1, 1024, 0, h->stream>>>(parts, stride, count, which, stats);
+  h->launches++;
+  B2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_merit_argmin(b200rbf_ctx* h, const double* fvals, const double* dmerit, long long m, const double* stats,
+                        int stats_negated, double w, double dtol, long long idx_off, void* pair_parts, int* nblocks) {
+  long long want = (m + kSelThreads - 1) / kSelThreads;
+  long long cap = (long long)h->sm_count * 8;
+  int blocks = (int)(want < cap ? want : cap);
+  if (blocks < 1) blocks = 1;
+  merit_argmin_kernel<<<blocks, kSelThreads, 0, h->stream>>>(fvals, dmerit, m, stats, stats_negated, w, dtol, idx_off,
+                                                            reinterpret_cast<Pair*>(pair_parts));
+  h->launches++;
+  B2_CUDA(cudaGetLastError());
+  *nblocks = blocks;
+  return 0;
+}
+
+int launch_pick(b200rbf_ctx* h, const void* pair_parts, int nparts, const double* cand, int d, double* fvals,
+                double* winner, int dpad, void* result_slot, void* pair_out) {
+  pick_kernel<<<1, kSelThreads, 0, h->stream>>>(reinterpret_cast<const Pair*>(pair_parts), nparts, cand, d, fvals,
+                                                winner, dpad, reinterpret_cast<Pair*>(result_slot),
+                                                reinterpret_cast<Pair*>(pair_out));
+  h->launches++;
+  B2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_take(b200rbf_ctx* h, const double* cand, int d, long long idx, double* fvals, double* winner, int dpad) {
+  take_kernel<<<1, 64, 0, h->stream>>>(cand, d, idx, fvals, winner, dpad);
+  h->launches++;
+  B2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_update(b200rbf_ctx* h, const double* cand, long long m, int d, const double* winner, double* dmerit,
+                  double* parts, int stride, int* count_out, bool exact) {
+  // rows per pass: as many as fit in ~96 KB of shared memory (2 CTAs per SM), at most kUpdRows
+  int rpp = (int)((96 * 1024 / sizeof(double) - d) / (size_t)(d | 1));
+  if (rpp > kUpdRows) rpp = kUpdRows;
+  B2_CHECK(rpp >= 1, B200RBF_EINVAL, "dimension %d too large for the distance-update kernel", d);
+  long long want = (m + rpp - 1) / rpp;
+  long long cap = (long long)h->sm_count * 4;
+  int blocks = (int)(want < cap ? want : cap);
+  if (blocks < 1) blocks = 1;
+  if (blocks > stride) blocks = stride;
+  const size_t smem = ((size_t)rpp * (d | 1) + d) * sizeof(double);
+  auto kern = exact ? update_kernel<true> : update_kernel<false>;
+  if (smem > 48 * 1024) B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<blocks, kUpdRows, smem, h->stream>>>(cand, m, d, winner, dmerit, parts, stride, rpp);
+  h->launches++;
+  B2_CUDA(cudaGetLastError());
+  *count_out = blocks;
+  return 0;
+}
+
+}  // namespace b200rbf

@@ -1,0 +1,146 @@
+"""GpuRBFInterpolant -- drop-in for pySOT.surrogate.RBFInterpolant (pySOT/surrogate/rbf.py:11-215) on one B200.
+
+Same constructor, attributes and methods; fit / predict / predict_deriv run in libb200rbf.so through ctypes.
+Strategies only ever call ``reset``, ``add_points`` and ``predict`` (surrogate_strategy.py:241-247, 429;
+candidate_srbf.py:39), all on the POAP controller thread.
+"""
+import os
+
+import numpy as np
+
+from . import _lib
+from .interface import (
+    HAVE_PYSOT, CubicKernel, Kernel, LinearTail, ReferenceRBFInterpolant, Surrogate, Tail, kernel_id, tail_id,
+)
+
+_Base = ReferenceRBFInterpolant if HAVE_PYSOT else Surrogate
+
+
+def default_device():
+    """LOCAL_RANK under torchrun (one process per GPU), else device 0."""
+    return int(os.environ.get("LOCAL_RANK", "0"))
+
+
+class GpuRBFInterpolant(_Base):
+    """RBF interpolant  s(x) = sum_j c_j phi(|u - u_j|) + lambda . p(u),  u = to_unit_box(x)  (rbf.py:12-32).
+
+    :param dim, lb, ub, output_transformation, kernel, tail, eta: as in the reference (rbf.py:67)
+    :param device: CUDA ordinal (default: LOCAL_RANK or 0)
+    :param exact_dist: accumulate squared distances with separate multiply and add exactly like
+        scipy's cdist instead of fused multiply-add (bit-identical distances, ~1.4x slower inner loop)
+
+    Differences a user can observe: ``A``, ``L``, ``U``, ``piv`` stay ``None`` (the factors live on the
+    device and every ``_fit`` is a fresh pivoted LU there instead of the incremental update of rbf.py:132-161),
+    and kernels / tails other than the reference's five classes raise ``NotImplementedError``.
+    """
+
+    def __init__(self, dim, lb, ub, output_transformation=None, kernel=None, tail=None, eta=1e-6, device=None,
+                 exact_dist=False):
+        if HAVE_PYSOT:
+            super().__init__(dim=dim, lb=lb, ub=ub, output_transformation=output_transformation, kernel=kernel,
+                             tail=tail, eta=eta)
+        else:
+            super().__init__(dim=dim, lb=lb, ub=ub, output_transformation=output_transformation)
+            if kernel is None or tail is None:  # rbf.py:70-72: BOTH are replaced if either is missing
+                kernel = CubicKernel()
+                tail = LinearTail(dim)
+            assert isinstance(kernel, Kernel) and isinstance(tail, Tail)
+            self.kernel = kernel
+            self.tail = tail
+            self.ntail = tail.dim_tail
+            self.A = self.L = self.U = self.piv = self.c = None
+            self.eta = eta
+            if kernel.order - 1 > tail.degree:  # rbf.py:85-86
+                raise ValueError("Kernel and tail mismatch")
+            assert self.dim == self.tail.dim
+        self._kid = kernel_id(self.kernel)
+        self._tid = tail_id(self.tail)
+        self._device = default_device() if device is None else int(device)
+        self._exact = bool(exact_dist)
+        self._handle = None
+        self.fit_seconds = None  # device time of the last fit (CUDA events)
+
+    # ------------------------------------------------------------------ device state
+    @property
+    def handle(self):
+        """The C handle, created on first use (after unpickling it is rebuilt lazily)."""
+        if self._handle is None:
+            self._handle = _lib.Handle(self._device)
+            if self._exact:
+                self._handle.set_option(_lib.OPT_EXACT_DIST, 1)
+        return self._handle
+
+    def __getstate__(self):
+        # CheckpointController dill-dumps the strategy, surrogate included, after every evaluation
+        # (controller.py:97-123, surrogate_strategy.py:166-180): drop the device handle, refit on demand.
+        state = self.__dict__.copy()
+        state["_handle"] = None
+        state["c"] = None
+        state["updated"] = False
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+
+    def reset(self):
+        """rbf.py:89-95."""
+        super().reset()
+        self.L = self.U = self.piv = self.c = None
+
+    # ------------------------------------------------------------------ fit
+    def _fit(self):
+        """Lazy fit (rbf.py:97-168): saddle-point assembly + pivoted LU + solves on the device."""
+        if self.updated:
+            return
+        assert self.num_pts >= self.ntail  # rbf.py:111
+        rhs = self.output_transformation(self.fX.copy())  # rbf.py:164
+        c, secs = self.handle.fit(self._X[: self.num_pts], rhs, self._kid, self._tid, self.eta)
+        self.c = c.reshape(-1, 1)
+        self.fit_seconds = secs
+        self.updated = True
+
+    def set_coefficients(self, c):
+        """Install coefficients computed elsewhere (a replica GPU of the sharded path, or a benchmark that
+        isolates scoring from fitting -- SURVEY appendix A) without fitting."""
+        c = np.asarray(c, dtype=np.float64).reshape(-1, 1)
+        assert c.shape[0] == self.num_pts + self.ntail
+        self.handle.load_model(self._X[: self.num_pts], c, self._kid, self._tid)
+        self.c = c
+        self.updated = True
+
+    # ------------------------------------------------------------------ evaluation
+    def _points(self, xx):
+        xx = np.atleast_2d(np.asarray(xx, dtype=np.float64))
+        if xx.shape[1] != self.dim:  # tails/*.py raise this from tail.eval; rbf.py:198-199 in predict_deriv
+            raise ValueError("Input has the wrong number of dimensions")
+        return xx
+
+    def predict(self, xx):
+        """(m, d) or (d,) points in the original domain -> (m, 1) predictions (rbf.py:170-185)."""
+        self._fit()
+        xx = self._points(xx)
+        return self.handle.predict(xx, self.lb, self.ub).reshape(-1, 1)
+
+    def predict_deriv(self, xx):
+        """(m, d) or (d,) -> (m, d) gradients w.r.t. the original coordinates (rbf.py:187-215)."""
+        self._fit()
+        xx = np.atleast_2d(np.asarray(xx, dtype=np.float64))
+        if xx.shape[1] != self.dim:
+            raise ValueError("Input has incorrect number of dimensions")
+        return self.handle.predict_deriv(xx, self.lb, self.ub)
+
+    def predict_device(self, x_dev, out_dev=None):
+        """Tensor hand-off: x_dev is a contiguous float64 CUDA tensor (m, d); returns a CUDA tensor (m, 1).
+        The kernels are enqueued on torch's current stream."""
+        import torch
+
+        self._fit()
+        assert x_dev.is_cuda and x_dev.dtype == torch.float64 and x_dev.is_contiguous() and x_dev.shape[1] == self.dim
+        if out_dev is None:
+            out_dev = torch.empty(x_dev.shape[0], dtype=torch.float64, device=x_dev.device)
+        self.handle.set_stream(torch.cuda.current_stream(x_dev.device).cuda_stream)
+        try:
+            self.handle.predict(x_dev, self.lb, self.ub, out=out_dev, m=x_dev.shape[0])
+        finally:
+            self.handle.set_stream(None)
+        return out_dev.reshape(-1, 1)

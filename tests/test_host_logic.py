@@ -1,0 +1,175 @@
+"""CPU: host-side mirror of the reference interface (pysot_b200/interface.py, rbf.py, candidates.py)."""
+import pickle
+
+import numpy as np
+import pytest
+
+from conftest import Problem
+import pysot_b200 as pb
+from pysot_b200 import candidates as cnd
+
+
+# ---- kernels / tails: the reference's known answers (tests/test_surrogates.py:37-112)
+def test_cubic_kernel():
+    k = pb.CubicKernel()
+    assert isinstance(k, pb.Kernel) and k.order == 2
+    np.testing.assert_allclose(k.eval(np.array(2)), 8)
+    np.testing.assert_allclose(k.deriv(np.array(2)), 12)
+    X = np.random.rand(10, 3)
+    np.testing.assert_allclose(k.eval(X), X ** 3)
+    np.testing.assert_allclose(k.deriv(X), 3 * X ** 2)
+
+
+def test_tps_kernel():
+    k = pb.TPSKernel()
+    assert isinstance(k, pb.Kernel) and k.order == 2
+    np.testing.assert_allclose(k.eval(np.array([2.0])), 4 * np.log(2))
+    np.testing.assert_allclose(k.deriv(np.array([2.0])), 2 * (1 + 2 * np.log(2)))
+    X = np.random.rand(10, 3)
+    np.testing.assert_allclose(k.eval(X.copy()), X ** 2 * np.log(X))
+    z = np.zeros(3)
+    assert np.all(np.isfinite(k.eval(z))) and z[0] == np.finfo(float).eps  # clamped in place (tps_kernel.py:28)
+
+
+def test_linear_kernel():
+    k = pb.LinearKernel()
+    assert isinstance(k, pb.Kernel) and k.order == 1
+    X = np.random.rand(10, 3)
+    np.testing.assert_allclose(k.eval(X), X)
+    np.testing.assert_allclose(k.deriv(X), np.ones((10, 3)))
+
+
+def test_tails():
+    lt = pb.LinearTail(1)
+    assert isinstance(lt, pb.Tail) and lt.degree == 1 and lt.dim_tail == 2
+    np.testing.assert_allclose(lt.eval(np.array([[2.0]])), np.array([[1, 2]]))
+    np.testing.assert_allclose(lt.deriv(np.array([[2.0]])), np.array([[0, 1]]))
+    lt = pb.LinearTail(3)
+    X = np.random.rand(10, 3)
+    np.testing.assert_allclose(lt.eval(X), np.hstack((np.ones((10, 1)), X)))
+    np.testing.assert_allclose(lt.deriv(X[0]), np.hstack((np.zeros((3, 1)), np.eye(3))))
+    with pytest.raises(ValueError):
+        lt.eval(np.random.rand(4, 2))
+    ct = pb.ConstantTail(3)
+    assert ct.degree == 0 and ct.dim_tail == 1
+    np.testing.assert_allclose(ct.eval(X), np.ones((10, 1)))
+    np.testing.assert_allclose(ct.deriv(X[0]), np.zeros((3, 1)))
+    with pytest.raises(ValueError):
+        ct.deriv(np.random.rand(1, 2))
+
+
+def test_median_capping():
+    x = np.array([[1.0], [5.0], [2.0], [9.0], [3.0]])
+    y = pb.median_capping(x)
+    assert np.array_equal(y.ravel(), [1, 3, 2, 3, 3]) and x[1, 0] == 5.0
+    assert pb.identity(x) is x
+
+
+# ---- surrogate bookkeeping (surrogate.py:33-74, rbf.py:67-95)
+def test_constructor_defaults_and_mismatch():
+    s = pb.GpuRBFInterpolant(dim=3, lb=np.zeros(3), ub=np.ones(3))
+    assert isinstance(s, pb.Surrogate)
+    assert type(s.kernel).__name__.endswith("CubicKernel") and s.ntail == 4 and s.eta == 1e-6
+    # either one missing -> BOTH replaced by the defaults (rbf.py:70-72)
+    s = pb.GpuRBFInterpolant(dim=3, lb=np.zeros(3), ub=np.ones(3), kernel=pb.TPSKernel())
+    assert type(s.kernel).__name__.endswith("CubicKernel")
+    with pytest.raises(ValueError, match="Kernel and tail mismatch"):
+        pb.GpuRBFInterpolant(dim=3, lb=np.zeros(3), ub=np.ones(3), kernel=pb.CubicKernel(), tail=pb.ConstantTail(3))
+    pb.GpuRBFInterpolant(dim=3, lb=np.zeros(3), ub=np.ones(3), kernel=pb.LinearKernel(), tail=pb.ConstantTail(3))
+    with pytest.raises(AssertionError):
+        pb.GpuRBFInterpolant(dim=3, lb=np.zeros(3), ub=np.ones(3), kernel=pb.CubicKernel(), tail=pb.LinearTail(2))
+
+
+def test_unsupported_kernel_has_no_fallback():
+    class Gauss(pb.Kernel):
+        order = 1
+
+        def eval(self, d):
+            return np.exp(-d ** 2)
+
+        def deriv(self, d):
+            return -2 * d * np.exp(-d ** 2)
+
+    with pytest.raises(NotImplementedError):
+        pb.GpuRBFInterpolant(dim=2, lb=np.zeros(2), ub=np.ones(2), kernel=Gauss(), tail=pb.LinearTail(2))
+
+
+def test_add_points_bookkeeping_and_reset():
+    lb, ub = np.array([0.0, -10.0]), np.array([100.0, 10.0])
+    s = pb.GpuRBFInterpolant(dim=2, lb=lb, ub=ub)
+    s.add_points(np.array([50.0, 0.0]), 3.0)            # float
+    s.add_points(np.array([[0.0, -10.0]]), np.array(4.0))  # 0-d
+    s.add_points(np.array([[100.0, 10.0], [25.0, 5.0]]), np.array([5.0, 6.0]))  # 1-d
+    s.add_points(np.array([[1.0, 1.0]]), np.array([[7.0]]))  # (k, 1)
+    assert s.num_pts == 5 and s.X.shape == (5, 2) and s.fX.shape == (5, 1) and not s.updated
+    np.testing.assert_allclose(s._X[:3], [[0.5, 0.5], [0, 0], [1, 1]])
+    with pytest.raises(AssertionError):
+        s.add_points(np.zeros((2, 2)), np.zeros(3))
+    s.reset()
+    assert s.num_pts == 0 and s.X.shape == (0, 2) and s.fX.shape == (0, 1) and s.c is None and not s.updated
+
+
+def test_pickle_drops_device_state():
+    s = pb.GpuRBFInterpolant(dim=2, lb=np.zeros(2), ub=np.ones(2), kernel=pb.TPSKernel(), tail=pb.LinearTail(2))
+    s.add_points(np.random.rand(6, 2), np.random.rand(6))
+    s.c, s.updated, s._handle = np.ones((9, 1)), True, object()
+    for mod in (pickle, __import__("dill")):
+        t = mod.loads(mod.dumps(s))
+        assert t._handle is None and t.c is None and t.updated is False
+        assert np.array_equal(t.X, s.X) and np.array_equal(t.fX, s.fX) and t._kid == 1 and t._tid == 0
+
+
+def test_merit_needs_gpu_surrogate():
+    class Fake:
+        pass
+
+    with pytest.raises(TypeError, match="no CPU fallback"):
+        pb.weighted_distance_merit(1, Fake(), np.zeros((2, 2)), np.zeros((2, 1)), np.zeros((4, 2)), [0.5])
+
+
+# ---- candidate generation consumes the global RNG exactly like the reference (fixtures from the live reference)
+def test_generators_match_reference_fixtures(candidate_cases):
+    for name in candidate_cases.names:
+        g = candidate_cases.get(name)
+        prob = Problem(g["lb"], g["ub"], g["int_var"])
+        kw = {k[3:]: (v.item() if v.ndim == 0 else v) for k, v in g.items() if k.startswith("kw_")}
+        if "subset" in kw:
+            kw["subset"] = list(np.atleast_1d(kw["subset"]))
+        gen = dict(dycors=cnd.generate_dycors, srbf=cnd.generate_srbf, uniform=cnd.generate_uniform)[str(g["kind"])]
+        np.random.seed(int(g["seed"]))
+        cand = gen(prob, g["X"], g["fX"], **kw)
+        assert np.array_equal(cand, g["cand"]), name
+
+
+def test_dycors_never_forces_last_coordinate():
+    """candidate_dycors.py:78: randint's upper bound is exclusive, so a forced perturbation never lands on the
+    last coordinate -- kept for seeded parity."""
+    prob = Problem(np.zeros(4), np.ones(4))
+    X = np.full((3, 4), 0.5)
+    np.random.seed(3)
+    cand = cnd.generate_dycors(prob, X, np.array([[1.0], [0.0], [2.0]]), prob_perturb=1e-9, num_cand=2000)
+    assert np.all((cand != 0.5).sum(axis=1) == 1)
+    assert np.all(cand[:, 3] == 0.5)
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir("/root/reference/pySOT"), reason="reference tree not present")
+def test_install_rebinds_reference_names():
+    from tools import ref_import
+
+    ref_import.load()
+    import pySOT.strategy.dycors_strategy as ds
+    import pySOT.strategy.srbf_strategy as ss
+    import pySOT.strategy.sop_strategy as so
+    import sys
+
+    cd = sys.modules["pySOT.auxiliary_problems.candidate_dycors"]  # the package attribute is the function
+
+    orig = ds.candidate_dycors
+    done = cnd.install()
+    try:
+        assert ds.candidate_dycors is cnd.candidate_dycors and so.candidate_dycors is cnd.candidate_dycors
+        assert ss.candidate_srbf is cnd.candidate_srbf and cd.weighted_distance_merit is cnd.weighted_distance_merit
+        assert len(done) >= 8
+    finally:
+        cnd.uninstall()
+    assert ds.candidate_dycors is orig
