@@ -1,0 +1,383 @@
+#!/usr/bin/env python3
+"""Benchmark of the hot path on BASELINE.json's headline workload (config #4: candidate acquisition sweep).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one full weighted_distance_merit pass (candidate_srbf.py:31-55) over one batch of DYCORS-shaped
+candidates: fused surrogate value + min distance + min/max statistics, then num_pts = 4 merit / argmin /
+distance-update rounds.  Workload: d = 50, n = 20 000 centers (Cubic kernel, linear tail, coefficients from a real
+fit of those centers), 2^20 candidates PER GPU (weak scaling; rows sharded over the ranks, centers replicated,
+NCCL moves only statistics, (merit, index) pairs and the winning row).
+
+metric   candidate x center pairs / s, whole job
+value    device-resident candidates (inputs in HBM before the timed region), CUDA events, max over ranks
+e2e      the public API call with HOST (pinned) candidate arrays: H2D of the batch and D2H of the picks inside
+roofline the fused score kernel against the FP64 FMA pipe, measured live (the path is FP64-compute-bound, see
+         DESIGN.md): achieved = pairs * (3d + 6) flops / kernel time; the HBM figure is reported beside it
+fit      BASELINE's second headline number: RBF fit seconds at N = 20 000 (TPS, d = 10), rank 0 only
+
+--impl reference times the CPU restatement of the reference (oracle/, same scipy/numpy routines as pySOT) on a
+bounded sample of the same workload with every host core.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+D, N_CENTERS, M_PER_GPU, NUM_PTS = 50, 20000, 1 << 20, 4
+WEIGHTS = [0.3, 0.5, 0.8, 0.95]
+DTOL = 1e-3
+FLOPS_PER_PAIR = 3 * D + 6  # sub + fma per coordinate, sqrt, phi (2), weight fma (2), running min
+WORKLOAD = "config#4 candidate acquisition: d=50, n=20000 centers, cubic+linear tail, 2^20 DYCORS candidates per GPU, num_pts=4"
+
+
+def make_centers():
+    rng = np.random.default_rng(0)
+    X = rng.random((N_CENTERS, D))
+    fX = (np.sin(3.0 * X.sum(axis=1)) + X[:, 0] ** 2)[:, None]
+    Xpend = np.random.default_rng(1).random((7, D))
+    return X, fX, Xpend
+
+
+def dycors_candidates_host(m, xbest, seed):
+    """DYCORS-shaped candidates (candidate_dycors.py:73-86 in distribution): prob_perturb 0.4, sigma 0.2, truncated
+    normal in [0, 1], rows with no perturbed coordinate get one in [0, d-2]."""
+    import scipy.stats as st
+
+    rng = np.random.default_rng(seed)
+    mask = rng.random((m, D)) < 0.4
+    none = np.where(mask.sum(axis=1) == 0)[0]
+    mask[none, rng.integers(0, D - 1, size=len(none))] = True
+    a, b = (0.0 - xbest) / 0.2, (1.0 - xbest) / 0.2
+    u = rng.random((m, D))
+    lo, hi = st.norm.cdf(a), st.norm.cdf(b)
+    z = st.norm.ppf(lo + u * (hi - lo))
+    return np.where(mask, np.clip(xbest + 0.2 * z, 0.0, 1.0), xbest)
+
+
+def dycors_candidates_device(m, xbest, seed, device):
+    """Same distribution generated on the device with torch's Philox generator (tensor hand-off, not product code)."""
+    import torch
+
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    xb = torch.from_numpy(xbest).to(device)
+    mask = torch.rand((m, D), generator=g, device=device, dtype=torch.float64) < 0.4
+    none = (mask.sum(dim=1) == 0).nonzero().ravel()
+    if none.numel() > 0:
+        mask[none, torch.randint(0, D - 1, (none.numel(),), generator=g, device=device)] = True
+    lo = torch.special.ndtr((0.0 - xb) / 0.2)
+    hi = torch.special.ndtr((1.0 - xb) / 0.2)
+    u = torch.rand((m, D), generator=g, device=device, dtype=torch.float64)
+    z = torch.special.ndtri(lo + u * (hi - lo))
+    return torch.where(mask, torch.clamp(xb + 0.2 * z, 0.0, 1.0), xb).contiguous()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = str(gpu_index), [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 9 and parts[0] == self.idx:
+                self.rows.append(parts)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        pw = [float(r[3]) for r in self.rows if r[3].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[5 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(self.rows), "reasons": reasons}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline
+def cpu_scoring_baseline(X, fX, Xpend, coef, xbest, budget_s=15.0, threads=None):
+    """The oracle port (same scipy cdist / numpy ufunc / dot calls as pySOT) on a bounded sample, all host threads."""
+    from oracle import rbf_oracle as orc
+
+    threads = threads or max(1, os.cpu_count() or 1)
+    o = orc.OracleRBF(D, np.zeros(D), np.ones(D))
+    o.add_points(X, fX)
+    o.c, o.updated = coef.reshape(-1, 1), True
+    chunk = 1024
+    probe = dycors_candidates_host(chunk * min(threads, 8), xbest, 11)
+    t0 = time.perf_counter()
+    orc.score_tiled(o, X, probe, Xpend, chunk=chunk, threads=threads)
+    rate = probe.shape[0] / (time.perf_counter() - t0)
+    m = int(min(max(rate * budget_s, chunk * threads), 1 << 19))
+    m = max(chunk, (m // chunk) * chunk)
+    cand = dycors_candidates_host(m, xbest, 12)
+    t0 = time.perf_counter()
+    fv, dm = orc.score_tiled(o, X, cand, Xpend, chunk=chunk, threads=threads)
+    orc.select_from_scores(cand, fv, dm, WEIGHTS, NUM_PTS, DTOL)
+    dt = time.perf_counter() - t0
+    return {"value": m * N_CENTERS / dt, "unit": "pairs/s", "cores": threads, "kind": "port",
+            "sample": "%d candidates x %d centers, d=%d, tiled reference path (%d-row chunks on a %d-thread pool), "
+                      "%.1f s" % (m, N_CENTERS, D, chunk, threads, dt), "seconds": dt, "m": m}
+
+
+def run_reference(args, rank):
+    """--impl reference: the CPU restatement of the reference, rank 0 only."""
+    if rank != 0:
+        return
+    X, fX, Xpend = make_centers()
+    coef = np.random.default_rng(2).standard_normal(N_CENTERS + D + 1)
+    xbest = X[np.argmin(fX)]
+    per_step = max(3.0, min(20.0, 90.0 / max(1, args.steps + args.warmup)))
+    vals = []
+    for s in range(args.warmup + args.steps):
+        r = cpu_scoring_baseline(X, fX, Xpend, coef, xbest, budget_s=per_step)
+        if s >= args.warmup:
+            vals.append(r)
+    tot_pairs = sum(r["m"] * N_CENTERS for r in vals)
+    tot_s = sum(r["seconds"] for r in vals)
+    v = tot_pairs / tot_s
+    cb = dict(vals[-1])
+    cb["value"] = v
+    print(json.dumps({
+        "impl": "reference", "metric": "candidate x center pairs/s", "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / len(vals), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "CPU reference path; each step is a bounded sample of the workload"},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------------ native arm
+def fit_benchmark(pb, sizes=(1000, 5000, 20000)):
+    """BASELINE config #3: TPS + linear tail, d = 10, X ~ U[0,1]^10 seed 0, fX = sin(3 sum X) + X0^2."""
+    out = []
+    for n in sizes:
+        rng = np.random.default_rng(0)
+        X = rng.random((n, 10))
+        fX = (np.sin(3.0 * X.sum(axis=1)) + X[:, 0] ** 2)[:, None]
+        s = pb.GpuRBFInterpolant(dim=10, lb=np.zeros(10), ub=np.ones(10), kernel=pb.TPSKernel(), tail=pb.LinearTail(10))
+        s.add_points(X, fX)
+        best_dev, best_wall = 1e30, 1e30
+        for _ in range(2 if n >= 20000 else 3):
+            s.updated = False
+            t0 = time.perf_counter()
+            s._fit()
+            best_wall = min(best_wall, time.perf_counter() - t0)
+            best_dev = min(best_dev, s.fit_seconds)
+        N = n + 11
+        flops = 2.0 / 3.0 * N ** 3 + 2.0 * N ** 2 + 0.5 * n * n * (3 * 10 + 4)
+        resid = float(np.max(np.abs(s.predict(X[:2000]) + s.eta * s.c[11:11 + min(n, 2000)] - fX[:2000])))
+        out.append({"n": n, "d": 10, "kernel": "tps", "seconds_device": best_dev, "seconds_host_to_host": best_wall,
+                    "tflops": flops / best_dev / 1e12, "interp_residual": resid})
+        del s
+    return out
+
+
+def run_native(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    import pysot_b200 as pb
+    from pysot_b200.sharded import GpuShardBackend, sharded_select, sharded_weighted_distance_merit
+
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    X, fX, Xpend = make_centers()
+    lb, ub = np.zeros(D), np.ones(D)
+    xbest = X[np.argmin(fX)]
+    rbf = pb.GpuRBFInterpolant(dim=D, lb=lb, ub=ub, device=local_rank)  # Cubic + LinearTail (reference default)
+    rbf.add_points(X, fX)
+    t0 = time.perf_counter()
+    rbf._fit()  # every rank fits its own replica (the fit does not shard: "replicas only")
+    fit50 = {"n": N_CENTERS, "d": D, "kernel": "cubic", "seconds_device": rbf.fit_seconds,
+             "seconds_host_to_host": time.perf_counter() - t0}
+    h = rbf.handle
+    Xdist = np.vstack((X, Xpend))
+
+    cand_dev = dycors_candidates_device(M_PER_GPU, xbest, 3 + rank, device)
+    cand_pin = torch.empty((M_PER_GPU, D), dtype=torch.float64, pin_memory=True)
+    cand_pin.copy_(cand_dev)
+    cand_host = cand_pin.numpy()
+    torch.cuda.synchronize()
+    backend = GpuShardBackend(rbf)
+
+    def step_device():
+        return sharded_select(backend, cand_dev, Xdist, True, WEIGHTS, NUM_PTS, DTOL)
+
+    def step_e2e():
+        return sharded_weighted_distance_merit(NUM_PTS, rbf, X, fX, cand_host, WEIGHTS, Xpend, DTOL)
+
+    # ---- value: device-resident inputs, CUDA events on the stream the kernels run on (torch's current stream)
+    for _ in range(args.warmup):
+        picks = step_device()
+    barrier()
+    sampler = ClockSampler(local_rank if os.environ.get("CUDA_VISIBLE_DEVICES") is None else
+                           os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank])
+    if rank == 0:
+        sampler.start()
+    l0 = h.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms = []
+    e0.record()
+    for _ in range(args.steps):
+        picks = step_device()
+        kernel_ms.append(h.last_score_ms)
+    e1.record()
+    barrier()
+    dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = sum_over_ranks(h.launches - l0)
+    clocks = sampler.stop() if rank == 0 else None
+    pairs_per_step = float(M_PER_GPU) * world * N_CENTERS
+    value = pairs_per_step * args.steps / (dev_ms * 1e-3)
+
+    # ---- e2e: public API, host (pinned) candidates, H2D + D2H inside, wall clock between device syncs
+    for _ in range(max(1, min(args.warmup, 2))):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        pts, idx = step_e2e()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = pairs_per_step * args.steps / e2e_s
+    h2d = M_PER_GPU * D * 8 + 7 * D * 8 + 2 * D * 8
+    d2h = NUM_PTS * (16 + D * 8) + 4 * 8
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (rank 0), peaks measured live on this device
+    peaks = h.fp64_peaks(ms=300.0)
+    mp, mp_kind = measured_peaks()
+    k_ms = float(np.mean(kernel_ms))
+    k_tflops = float(M_PER_GPU) * N_CENTERS * FLOPS_PER_PAIR / (k_ms * 1e-3) / 1e12
+    alg_bytes = M_PER_GPU * (8 * D + 16)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "score_kernel_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {
+        "kernel": "score_kernel<DPAD=50, cubic, fma>", "bound": "fp64_fma", "achieved": k_tflops,
+        "peak": peaks["dfma_tflops"], "unit": "TFLOP/s", "frac": k_tflops / peaks["dfma_tflops"],
+        "peak_source": "b200rbf_fp64_peaks: dependency-free DFMA loop on this device, 300 ms (MEASURED_PEAKS.json has no fp64 entry)",
+        "flops_per_pair": FLOPS_PER_PAIR, "launch_ms": k_ms, "share_of_step": k_ms * args.steps / dev_ms,
+        "dmma_peak_tflops": peaks["dmma_tflops"], "traffic": traffic,
+        "hbm": {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (k_ms * 1e-3) / 1e9, "peak_gbs": mp["hbm_gbs"],
+                "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / mp["hbm_gbs"], "peak_kind": mp_kind},
+    }
+    line = {
+        "metric": "candidate x center pairs/s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_candidates": M_PER_GPU * world, "centers": N_CENTERS, "dim": D,
+                   "num_pts": NUM_PTS, "parallelism": "candidate rows sharded x%d, centers replicated" % world,
+                   "l2": "inputs larger than L2 (419 MB of candidates per GPU per step)"},
+        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": 1e3 * e2e_s / args.steps},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "picked": [int(i) for i in picks[0]],
+        "fit_d50": fit50,
+    }
+    if world == 1 and not args.skip_extras:
+        coef = rbf.c.ravel().copy()
+        line["cpu_baseline"] = {k: v for k, v in cpu_scoring_baseline(X, fX, Xpend, coef, xbest).items()
+                                if k in ("value", "unit", "cores", "kind", "sample")}
+        fits = fit_benchmark(pb)
+        for f in fits:
+            f["frac_of_dmma_peak"] = f["tflops"] / peaks["dmma_tflops"]
+        line["fit"] = fits
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--skip-extras", action="store_true", help="skip the CPU baseline and the fit sweep")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-launch ourselves as one process per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.abspath(__file__), "--gpus", str(args.gpus),
+               "--steps", str(args.steps), "--warmup", str(args.warmup)] + (["--skip-extras"] if args.skip_extras else [])
+        sys.exit(subprocess.call(cmd))
+    run_native(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -121,11 +121,15 @@ int b200rbf_shard_update(b200rbf_handle h, const double* winner_dev);
 
 /* Measured FP64 ceilings of this device, used as roofline denominators by bench.py: a dependent-free
  * DFMA loop and an mma.sync m8n8k4 f64 (DMMA) loop, full grid, `ms` milliseconds each.
- * out[0] = DFMA TFLOP/s, out[1] = DMMA TFLOP/s. */
+ * out[0] = DFMA TFLOP/s, out[1] = DMMA TFLOP/s, out[2] = combined TFLOP/s when every warp interleaves both
+ * (tells whether the FP64 tensor op has its own datapath).  out must hold 3 doubles. */
 int b200rbf_fp64_peaks(b200rbf_handle h, double ms, double* out);
 
 /* Counters: number of kernels this handle launched since creation (bench.py's gpu_launches). */
 long long b200rbf_launch_count(b200rbf_handle h);
+/* Device time (ms, CUDA events on the handle's stream) of the fused score kernel(s) of the last b200rbf_score;
+ * with host candidates it spans the chunk pipeline including the waits on the H2D copies. */
+double b200rbf_last_score_ms(b200rbf_handle h);
 
 /* ---- test hooks: exercise the factorisation pieces in isolation (tests/ only, not the drop-in surface) ----
  * dbg_lu  : A_host is N x (N + nrhs) row-major; on return the leading N x N block holds L\U (unit lower L),

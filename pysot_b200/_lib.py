@@ -38,6 +38,7 @@ PROTOTYPES = {
     "b200rbf_shard_update": (C.c_int, [_vp, _vp]),
     "b200rbf_fp64_peaks": (C.c_int, [_vp, C.c_double, _vp]),
     "b200rbf_launch_count": (C.c_longlong, [_vp]),
+    "b200rbf_last_score_ms": (C.c_double, [_vp]),
     "b200rbf_dbg_lu": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp]),
     "b200rbf_dbg_gemm": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _dp]),
 }
@@ -125,6 +126,10 @@ class Handle:
     def launches(self):
         return int(load().b200rbf_launch_count(self._h))
 
+    @property
+    def last_score_ms(self):
+        return float(load().b200rbf_last_score_ms(self._h))
+
     # ---- model
     def fit(self, Xu, rhs, kernel, tail, eta):
         Xu, rhs = f64(Xu), f64(rhs).ravel()
@@ -199,9 +204,9 @@ class Handle:
 
     # ---- measurement / test hooks
     def fp64_peaks(self, ms=200.0):
-        out = np.zeros(2)
+        out = np.zeros(3)
         check(load().b200rbf_fp64_peaks(self._h, float(ms), ptr(out)))
-        return {"dfma_tflops": float(out[0]), "dmma_tflops": float(out[1])}
+        return {"dfma_tflops": float(out[0]), "dmma_tflops": float(out[1]), "dfma_plus_dmma_tflops": float(out[2])}
 
     def dbg_lu(self, A, nrhs=0):
         A = f64(A).copy()

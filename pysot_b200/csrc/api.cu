@@ -79,7 +79,7 @@ int check_model_args(int n, int d, int kernel, int tail) {
   const int order = (kernel == B200RBF_KERNEL_LINEAR) ? 1 : 2;
   const int degree = (tail == B200RBF_TAIL_LINEAR) ? 1 : 0;
   B2_CHECK(order - 1 <= degree, B200RBF_EINVAL, "Kernel and tail mismatch");
-  B2_CHECK(pad_dim(d) <= kMaxRegDim, B200RBF_EINVAL, "dim %d > %d is not supported by this build", d, kMaxRegDim);
+  B2_CHECK(pad_dim(d) <= kGenMaxDim, B200RBF_EINVAL, "dim %d > %d is not supported by this build", d, kGenMaxDim);
   return 0;
 }
 
@@ -142,7 +142,11 @@ struct ScorePlan {
   int dist_mode = 0;          // min_mode of the distance-only pass (1 write, 2 combine)
 };
 
+// candidates per CTA of the kernel that serves this padded dimension
+int block_rows(int dpad) { return dpad <= kMaxRegDim ? kScoreThreads : score_generic_threads(); }
+
 int launch_score_any(b200rbf_ctx* h, const ScoreArgs& a, int dpad, int kernel, bool exact, bool with_phi) {
+  if (dpad > kMaxRegDim) return launch_score_generic(h, a, dpad, kernel, exact, with_phi);
   switch ((dpad - 2) / 8) {
     case 0: return launch_score_group0(h, a, dpad, kernel, exact, with_phi);
     case 1: return launch_score_group1(h, a, dpad, kernel, exact, with_phi);
@@ -207,7 +211,7 @@ int score_pipeline(b200rbf_ctx* h, const ScorePlan& plan, const double* cand, lo
   const Model& M = h->model;
   const PtrKind kind = ptr_kind(cand);
   if (kind == kDevice) {
-    const long long kMaxRows = (long long)kScoreThreads * 0x7fff0000LL;
+    const long long kMaxRows = (long long)block_rows(M.dpad) * 0x7fff0000LL;
     B2_CHECK(m <= kMaxRows, B200RBF_EINVAL, "too many candidates");
     B2_TRY(score_rows(h, plan, cand, 0, m, box, fvals, dmerit, parts, nparts, 0));
     *cand_dev_out = cand;
@@ -236,18 +240,18 @@ int score_pipeline(b200rbf_ctx* h, const ScorePlan& plan, const double* cand, lo
     used[slot] = true;
     B2_CUDA(cudaStreamWaitEvent(h->stream, h->ev_copy[slot], 0));
     B2_TRY(score_rows(h, plan, dst_dev, r0, rows, box, fvals, dmerit, parts, nparts, part_off));
-    part_off += (int)((rows + kScoreThreads - 1) / kScoreThreads);
+    part_off += (int)((rows + block_rows(M.dpad) - 1) / block_rows(M.dpad));
   }
   *cand_dev_out = dst_dev;
   return 0;
 }
 
-int count_parts(long long m, long long chunk, bool chunked) {
-  if (!chunked) return (int)((m + kScoreThreads - 1) / kScoreThreads);
+int count_parts(long long m, long long chunk, bool chunked, int br) {
+  if (!chunked) return (int)((m + br - 1) / br);
   long long total = 0;
   for (long long r0 = 0; r0 < m; r0 += chunk) {
     const long long rows = (m - r0 < chunk) ? (m - r0) : chunk;
-    total += (rows + kScoreThreads - 1) / kScoreThreads;
+    total += (rows + br - 1) / br;
   }
   return (int)total;
 }
@@ -288,6 +292,8 @@ int b200rbf_create(int device, b200rbf_handle* out) {
   for (int i = 0; i < 2; ++i) B2_CUDA(cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming));
   B2_CUDA(cudaEventCreate(&h->ev_t0));
   B2_CUDA(cudaEventCreate(&h->ev_t1));
+  B2_CUDA(cudaEventCreate(&h->ev_s0));
+  B2_CUDA(cudaEventCreate(&h->ev_s1));
   B2_CUDA(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
   *out = h;
   return 0;
@@ -309,6 +315,7 @@ int b200rbf_destroy(b200rbf_handle h) {
   h->stage[0].release(); h->stage[1].release(); h->pin_small.release();
   for (int i = 0; i < 2; ++i) cudaEventDestroy(h->ev_copy[i]);
   cudaEventDestroy(h->ev_t0); cudaEventDestroy(h->ev_t1); cudaEventDestroy(h->ev_done);
+  cudaEventDestroy(h->ev_s0); cudaEventDestroy(h->ev_s1);
   cudaStreamDestroy(h->own_stream);
   cudaStreamDestroy(h->copy_stream);
   delete h;
@@ -339,6 +346,7 @@ int b200rbf_set_option(b200rbf_handle h, int option, long long value) {
 }
 
 long long b200rbf_launch_count(b200rbf_handle h) { return h ? h->launches : 0; }
+double b200rbf_last_score_ms(b200rbf_handle h) { return h ? h->last_score_ms : -1.0; }
 
 int b200rbf_load(b200rbf_handle h, const double* Xu, const double* c, int n, int d, int kernel, int tail) {
   B2_CHECK(h && Xu && c, B200RBF_EINVAL, "NULL argument");
@@ -401,7 +409,7 @@ int b200rbf_predict(b200rbf_handle h, const double* x, long long m, const double
   const Model& M = h->model;
   B2_TRY(upload_box(h, lb, ub, M.d, M.dpad, h->tmp_box, nullptr, nullptr));
   const bool host_in = ptr_kind(x) != kDevice, host_out = ptr_kind(out) != kDevice;
-  const int nparts = count_parts(m, h->chunk_rows, host_in);
+  const int nparts = count_parts(m, h->chunk_rows, host_in, block_rows(M.dpad));
   size_t need = (size_t)4 * nparts * sizeof(double) + 64;
   const size_t off_f = need;
   if (host_out) need += (size_t)m * sizeof(double);
@@ -486,7 +494,7 @@ int b200rbf_score(b200rbf_handle h, const double* cand, long long m, const doubl
   }
 
   const bool host_in = ptr_kind(cand) != kDevice;
-  const int nparts = count_parts(m, h->chunk_rows, host_in);
+  const int nparts = count_parts(m, h->chunk_rows, host_in, block_rows(M.dpad));
   S.nparts = nparts > h->sm_count * 8 ? nparts : h->sm_count * 8;  // also holds the update kernel's partials
   B2_TRY(S.parts.reserve((size_t)4 * S.nparts * sizeof(double)));
   B2_TRY(S.fvals.reserve((size_t)m * sizeof(double)));
@@ -499,8 +507,10 @@ int b200rbf_score(b200rbf_handle h, const double* cand, long long m, const doubl
     B2_TRY(S.cand_own.reserve((size_t)m * M.d * sizeof(double)));
     own = S.cand_own.as<double>();
   }
+  B2_CUDA(cudaEventRecord(h->ev_s0, h->stream));
   B2_TRY(score_pipeline(h, plan, cand, m, own, S.box.as<double>(), S.fvals.as<double>(), S.dmerit.as<double>(),
                         S.parts.as<double>(), S.nparts, &S.cand));
+  B2_CUDA(cudaEventRecord(h->ev_s1, h->stream));
   B2_TRY(launch_stats(h, S.parts.as<double>(), S.nparts, nparts, 3, S.stats.as<double>()));
   S.m = m;
   S.d = M.d;
@@ -508,6 +518,11 @@ int b200rbf_score(b200rbf_handle h, const double* cand, long long m, const doubl
   if (dmerit_out) B2_TRY(copy_out(h, dmerit_out, S.dmerit.p, (size_t)m * sizeof(double)));
   if (stats_out) B2_TRY(copy_out(h, stats_out, S.stats.p, 4 * sizeof(double)));
   B2_CUDA(cudaStreamSynchronize(h->stream));
+  {
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, h->ev_s0, h->ev_s1) != cudaSuccess) cudaGetLastError();
+    h->last_score_ms = ms;
+  }
   S.valid = true;
   return 0;
 }

@@ -92,12 +92,29 @@ struct PinBuf {
 };
 
 // ---------------------------------------------------------------- constants
-constexpr int kMaxRegDim = 64;     // candidate coordinates held in registers up to this (padded) dimension
-constexpr int kScoreThreads = 256; // threads (= candidates) per CTA in the score kernels
-constexpr int kTileRows = 32;      // center rows per shared-memory tile (TMA bulk copy granule)
-constexpr int kStages = 3;         // tile ring depth
-constexpr int kJT = 4;             // centers processed together per thread (independent accumulators)
-constexpr int kMaxParts = 1 << 20; // upper bound on per-CTA partial slots
+// tiling of the score kernels; the -D overrides exist for tools/k2_tune.cu (measured choices: DESIGN.md)
+#ifndef B2_SCORE_THREADS
+#define B2_SCORE_THREADS 128
+#endif
+#ifndef B2_SCORE_MINB
+#define B2_SCORE_MINB 3
+#endif
+#ifndef B2_TILE_ROWS
+#define B2_TILE_ROWS 32
+#endif
+#ifndef B2_STAGES
+#define B2_STAGES 3
+#endif
+#ifndef B2_JT
+#define B2_JT 4
+#endif
+constexpr int kMaxRegDim = 64;                  // candidate coordinates held in registers up to this (padded) dimension
+constexpr int kScoreThreads = B2_SCORE_THREADS; // threads (= candidates) per CTA in the score kernels
+constexpr int kScoreMinBlocks = B2_SCORE_MINB;  // __launch_bounds__ min CTAs per SM (register cap)
+constexpr int kTileRows = B2_TILE_ROWS;         // center rows per shared-memory tile (TMA bulk copy granule)
+constexpr int kStages = B2_STAGES;              // tile ring depth
+constexpr int kJT = B2_JT;                      // centers processed together per thread (independent accumulators)
+constexpr int kGenMaxDim = 192;                 // largest padded dimension of the shared-memory (generic) score kernel
 
 inline int pad_dim(int d) { return (d + 1) & ~1; }                       // even: rows are multiples of 16 B
 inline int pad_rows(int n) { return ((n + kJT - 1) / kJT) * kJT; }       // multiples of kJT (duplicates of last row)
@@ -145,6 +162,8 @@ struct b200rbf_ctx {
   int sm_count = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_t0 = nullptr, ev_t1 = nullptr, ev_done = nullptr;
+  cudaEvent_t ev_s0 = nullptr, ev_s1 = nullptr;  // around the fused score kernel(s) of the last b200rbf_score
+  double last_score_ms = -1.0;
   b200rbf::PinBuf stage[2];
   b200rbf::PinBuf pin_small;
   long long launches = 0;
@@ -180,6 +199,9 @@ struct ScoreArgs {
   int part_off;            // first partial slot of this launch
 };
 
+// score kernel for kMaxRegDim < dpad <= kGenMaxDim (score_generic.cu) and its candidates-per-CTA
+int launch_score_generic(b200rbf_ctx* h, const ScoreArgs& a, int dpad, int kernel, bool exact, bool with_phi);
+int score_generic_threads();
 // parts: 4 rows {fmin, fmax, dmin, dmax} x `stride` slots, `count` of them valid; which: bit0 f rows, bit1 d rows
 int launch_stats(b200rbf_ctx* h, const double* parts, int stride, int count, int which, double* stats);
 int launch_merit_argmin(b200rbf_ctx* h, const double* fvals, const double* dmerit, long long m, const double* stats,

@@ -509,6 +509,29 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters, 
   if (s == 123.456) out[0] = s;
 }
 
+// both at once: every warp interleaves 8 independent DFMA chains with 8 independent DMMA chains.  If the FP64
+// tensor op had its own datapath the combined rate would exceed either peak; it does not.
+__global__ void __launch_bounds__(256) dmix_peak_kernel(double* out, int iters, double seed) {
+  double acc[8][2], f[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    acc[i][0] = acc[i][1] = seed;
+    f[i] = seed + i + threadIdx.x * 1e-9;
+  }
+  const double a = 1.0 + 1e-12 * threadIdx.x, b = 1e-15, m = 1.0 + 1e-12;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      dmma_884(acc[i][0], acc[i][1], a, b);
+      f[i] = fma(f[i], m, b);
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += acc[i][0] + acc[i][1] + f[i];
+  if (s == 123.456) out[0] = s;
+}
+
 }  // namespace
 
 // =================================================================================================== host side
@@ -683,15 +706,17 @@ int run_fp64_peaks(b200rbf_ctx* h, double ms, double* out) {
   cudaEvent_t e0, e1;
   B2_CUDA(cudaEventCreate(&e0));
   B2_CUDA(cudaEventCreate(&e1));
-  for (int which = 0; which < 2; ++which) {
+  for (int which = 0; which < 3; ++which) {
     int iters = 2000;
     float t = 0.f;
     for (int rep = 0; rep < 3; ++rep) {  // calibrate, then run ~ms
       B2_CUDA(cudaEventRecord(e0, h->stream));
       if (which == 0)
         dfma_peak_kernel<<<blocks, 256, 0, h->stream>>>(sink.as<double>(), iters, 1.0);
-      else
+      else if (which == 1)
         dmma_peak_kernel<<<blocks, 256, 0, h->stream>>>(sink.as<double>(), iters, 1.0);
+      else
+        dmix_peak_kernel<<<blocks, 256, 0, h->stream>>>(sink.as<double>(), iters, 1.0);
       h->launches++;
       B2_CUDA(cudaEventRecord(e1, h->stream));
       B2_CUDA(cudaEventSynchronize(e1));
@@ -707,8 +732,10 @@ int run_fp64_peaks(b200rbf_ctx* h, double ms, double* out) {
     double flops;
     if (which == 0)
       flops = threads * 8.0 * 2.0 * iters;             // 8 FMAs per iteration per thread
-    else
+    else if (which == 1)
       flops = (threads / 32.0) * 8.0 * 512.0 * iters;  // 8 m8n8k4 MMAs (8*8*4*2 flops) per iteration per warp
+    else
+      flops = threads * 8.0 * 2.0 * iters + (threads / 32.0) * 8.0 * 512.0 * iters;
     out[which] = flops / (t * 1e-3) / 1e12;
   }
   cudaEventDestroy(e0);

@@ -84,7 +84,7 @@ struct TileSmem {
 };
 
 template <int DPAD, int KERN, bool EXACT, bool WITH_PHI>
-__global__ void __launch_bounds__(kScoreThreads) score_kernel(ScoreArgs a) {
+__global__ void __launch_bounds__(kScoreThreads, kScoreMinBlocks) score_kernel(ScoreArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* s_pts = reinterpret_cast<double*>(smem_raw);
   double* s_wts = s_pts + (size_t)kStages * kTileRows * DPAD;

@@ -71,7 +71,7 @@ def test_pivoted_lu_against_numpy(pb, N):
     h = _lib.Handle(0)
     rng = np.random.default_rng(N)
     A = rng.standard_normal((N, N))
-    if N > 4:
+    if N > 8:
         A[:3, :3] = 0.0  # zero leading block like the saddle-point system: pivoting is mandatory
     b = rng.standard_normal((N, 1))
     LU, ipiv, info = h.dbg_lu(np.hstack((A, b)), nrhs=1)
@@ -379,3 +379,28 @@ def test_properties_at_scale(pb):
     # permutation of the candidates permutes the scores
     perm = rng.permutation(4096)
     assert np.array_equal(s.predict(cand[:4096][perm]).ravel(), fv2[perm])
+
+
+@pytest.mark.parametrize("d", [66, 101])
+def test_dimensions_above_64_use_the_generic_kernel(pb, orc, d):
+    """padded dim > 64: candidate coordinates in shared memory instead of registers (score_generic.cu)."""
+    rng = np.random.default_rng(d)
+    n, m = d + 40, 3000
+    lb, ub = -np.ones(d), np.ones(d) * 1.5
+    X = lb + (ub - lb) * rng.random((n, d))
+    fX = np.sin(X.sum(1) / 5)[:, None]
+    Xpend = lb + (ub - lb) * rng.random((2, d))
+    cand = lb + (ub - lb) * rng.random((m, d))
+    for kernel in ("cubic", "tps"):
+        s = make_gpu(pb, d, lb, ub, kernel, "linear", exact_dist=True)
+        s.add_points(X, fX)
+        o = orc.OracleRBF(d, lb, ub, kernel, "linear")
+        o.add_points(X, fX)
+        tr = {}
+        orc.weighted_distance_merit(3, o, X, fX, cand.copy(), [0.3, 0.5, 0.8], Xpend, 1e-3, trace=tr)
+        idx, _, fv, dm, _ = pb.merit_select_indices(3, s, X, cand, [0.3, 0.5, 0.8], Xpend, want_scores=True)
+        assert relmax(fv, tr["fvals_raw"].ravel()) < TOL and relmax(dm, tr["dmerit0"].ravel()) < 1e-13
+        assert np.array_equal(idx, tr["picked"])
+        assert relmax(s.predict_deriv(cand[:5]), o.predict_deriv(cand[:5])) < TOL
+    with pytest.raises(ValueError):
+        pb.GpuRBFInterpolant(dim=500, lb=np.zeros(500), ub=np.ones(500)).add_points(np.zeros((501, 500)), np.zeros(501))
