@@ -58,8 +58,10 @@ int b200rbf_version(void);
  * candidate workspace until destroy. */
 int b200rbf_create(int device, b200rbf_handle* out);
 int b200rbf_destroy(b200rbf_handle h);
-/* cudaStream_t to enqueue on (e.g. torch.cuda.current_stream().cuda_stream); NULL = handle's own stream. */
-int b200rbf_set_stream(b200rbf_handle h, void* cuda_stream);
+/* Stream the handle enqueues on.  use_own != 0: the handle's private non-blocking stream (the default).
+ * use_own == 0: cuda_stream is taken literally, e.g. torch.cuda.current_stream().cuda_stream -- note that torch's
+ * default stream IS the NULL (legacy default) stream, so NULL is a valid value here, not "unset". */
+int b200rbf_set_stream(b200rbf_handle h, void* cuda_stream, int use_own);
 int b200rbf_set_option(b200rbf_handle h, int option, long long value);
 
 /* RBFInterpolant._fit, initial branch + coefficient solve (rbf.py:110-130, 164-168):

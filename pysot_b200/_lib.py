@@ -24,7 +24,7 @@ PROTOTYPES = {
     "b200rbf_version": (C.c_int, []),
     "b200rbf_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "b200rbf_destroy": (C.c_int, [_vp]),
-    "b200rbf_set_stream": (C.c_int, [_vp, _vp]),
+    "b200rbf_set_stream": (C.c_int, [_vp, _vp, C.c_int]),
     "b200rbf_set_option": (C.c_int, [_vp, C.c_int, C.c_longlong]),
     "b200rbf_fit": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _vp, _dp]),
     "b200rbf_load": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int]),
@@ -117,7 +117,12 @@ class Handle:
 
     # ---- configuration
     def set_stream(self, stream_ptr):
-        check(load().b200rbf_set_stream(self._h, stream_ptr))
+        """stream_ptr: a cudaStream_t as int (0 is the legacy default stream, which is torch's default), or None
+        to go back to the handle's private stream."""
+        if stream_ptr is None:
+            check(load().b200rbf_set_stream(self._h, None, 1))
+        else:
+            check(load().b200rbf_set_stream(self._h, int(stream_ptr), 0))
 
     def set_option(self, option, value):
         check(load().b200rbf_set_option(self._h, int(option), int(value)))

@@ -322,9 +322,9 @@ int b200rbf_destroy(b200rbf_handle h) {
   return 0;
 }
 
-int b200rbf_set_stream(b200rbf_handle h, void* s) {
+int b200rbf_set_stream(b200rbf_handle h, void* s, int use_own) {
   B2_CHECK(h != nullptr, B200RBF_EINVAL, "handle is NULL");
-  h->stream = s ? reinterpret_cast<cudaStream_t>(s) : h->own_stream;
+  h->stream = use_own ? h->own_stream : reinterpret_cast<cudaStream_t>(s);
   return 0;
 }
 

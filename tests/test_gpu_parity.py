@@ -402,5 +402,7 @@ def test_dimensions_above_64_use_the_generic_kernel(pb, orc, d):
         assert relmax(fv, tr["fvals_raw"].ravel()) < TOL and relmax(dm, tr["dmerit0"].ravel()) < 1e-13
         assert np.array_equal(idx, tr["picked"])
         assert relmax(s.predict_deriv(cand[:5]), o.predict_deriv(cand[:5])) < TOL
-    with pytest.raises(ValueError):
-        pb.GpuRBFInterpolant(dim=500, lb=np.zeros(500), ub=np.ones(500)).add_points(np.zeros((501, 500)), np.zeros(501))
+    big = pb.GpuRBFInterpolant(dim=500, lb=np.zeros(500), ub=np.ones(500))
+    big.add_points(rng.random((501, 500)), np.zeros(501))
+    with pytest.raises(ValueError):  # beyond the generic kernel's shared-memory budget: refused, never a CPU fallback
+        big.predict(np.zeros(500))
