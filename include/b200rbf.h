@@ -48,7 +48,9 @@ enum {
   /* rows per host->device chunk of the candidate pipeline (default 65536)                              */
   B200RBF_OPT_CHUNK_ROWS = 2,
   /* LU panel width (default 128; multiple of 32)                                                       */
-  B200RBF_OPT_LU_PANEL = 3
+  B200RBF_OPT_LU_PANEL = 3,
+  /* 1 (default): factor panel k+1 on a second, high-priority stream while the rest of trailing update k runs  */
+  B200RBF_OPT_LU_LOOKAHEAD = 4
 };
 
 const char* b200rbf_last_error(void);

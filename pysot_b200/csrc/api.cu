@@ -292,6 +292,13 @@ int b200rbf_create(int device, b200rbf_handle* out) {
   for (int i = 0; i < 2; ++i) B2_CUDA(cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming));
   B2_CUDA(cudaEventCreate(&h->ev_t0));
   B2_CUDA(cudaEventCreate(&h->ev_t1));
+  {
+    int lo = 0, hi = 0;  // numerically lower = higher priority
+    B2_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    B2_CUDA(cudaStreamCreateWithPriority(&h->la_stream, cudaStreamNonBlocking, hi));
+    B2_CUDA(cudaEventCreateWithFlags(&h->ev_la1, cudaEventDisableTiming));
+    B2_CUDA(cudaEventCreateWithFlags(&h->ev_la2, cudaEventDisableTiming));
+  }
   B2_CUDA(cudaEventCreate(&h->ev_s0));
   B2_CUDA(cudaEventCreate(&h->ev_s1));
   B2_CUDA(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
@@ -316,6 +323,9 @@ int b200rbf_destroy(b200rbf_handle h) {
   for (int i = 0; i < 2; ++i) cudaEventDestroy(h->ev_copy[i]);
   cudaEventDestroy(h->ev_t0); cudaEventDestroy(h->ev_t1); cudaEventDestroy(h->ev_done);
   cudaEventDestroy(h->ev_s0); cudaEventDestroy(h->ev_s1);
+  cudaEventDestroy(h->ev_la1); cudaEventDestroy(h->ev_la2);
+  cudaStreamSynchronize(h->la_stream);
+  cudaStreamDestroy(h->la_stream);
   cudaStreamDestroy(h->own_stream);
   cudaStreamDestroy(h->copy_stream);
   delete h;
@@ -336,6 +346,7 @@ int b200rbf_set_option(b200rbf_handle h, int option, long long value) {
       B2_CHECK(value >= 256, B200RBF_EINVAL, "chunk rows must be >= 256");
       h->chunk_rows = value;
       return 0;
+    case B200RBF_OPT_LU_LOOKAHEAD: h->lu_lookahead = value != 0; return 0;
     case B200RBF_OPT_LU_PANEL:
       B2_CHECK(value >= 32 && value <= 128 && value % 32 == 0, B200RBF_EINVAL, "LU panel must be 32, 64, 96 or 128");
       h->lu_panel = (int)value;

@@ -164,6 +164,10 @@ struct b200rbf_ctx {
   cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_t0 = nullptr, ev_t1 = nullptr, ev_done = nullptr;
   cudaEvent_t ev_s0 = nullptr, ev_s1 = nullptr;  // around the fused score kernel(s) of the last b200rbf_score
   double last_score_ms = -1.0;
+  // LU look-ahead: panel k+1 factors on a high-priority stream while the rest of trailing update k runs
+  cudaStream_t la_stream = nullptr;
+  cudaEvent_t ev_la1 = nullptr, ev_la2 = nullptr;
+  bool lu_lookahead = true;
   b200rbf::PinBuf stage[2];
   b200rbf::PinBuf pin_small;
   long long launches = 0;

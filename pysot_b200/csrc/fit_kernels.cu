@@ -324,10 +324,17 @@ __global__ void __launch_bounds__(128) trsm32_kernel(double* __restrict__ A, int
 
 // ------------------------------------------------------------------------------------------------ DMMA GEMM
 // C[M x Nc] -= A[M x K] * B[K x Nc], all row-major.  K % 16 == 0; pointers / leading dims 16-byte aligned.
-constexpr int kGemmBM = 128, kGemmBN = 128, kGemmBK = 16, kGemmThreads = 256;
+//
+// CTA tile 128 x 64, 256 threads = 8 warps as 4 (M) x 2 (N), warp tile 32 x 32 = 4 x 4 m8n8k4 accumulators (64
+// registers), so two CTAs fit one SM and one CTA's prologue / epilogue hides behind the other's main loop.
+// Operands stream through a 3-stage cp.async ring with ONE barrier per k-step.  The C tile is loaded into the
+// accumulators up front (its latency hides behind the first k-steps) and A fragments are negated on the way in,
+// so acc = C - A B accumulates directly and the epilogue is store-only.
+constexpr int kGemmBM = 128, kGemmBN = 64, kGemmBK = 16, kGemmThreads = 256, kGemmStages = 3;
 constexpr int kGemmLdA = kGemmBK + 4;   // 20 doubles: 4 consecutive rows x 4 k hit 16 distinct bank pairs
-constexpr int kGemmLdB = kGemmBN + 4;   // 132 doubles: same for 4 k x 4 columns
-constexpr size_t kGemmSmem = 2 * (size_t)(kGemmBM * kGemmLdA + kGemmBK * kGemmLdB) * sizeof(double);
+constexpr int kGemmLdB = kGemmBN + 4;   // 68 doubles (68 mod 16 == 4): same for 4 k x 4 columns
+constexpr int kGemmStageDoubles = kGemmBM * kGemmLdA + kGemmBK * kGemmLdB;
+constexpr size_t kGemmSmem = (size_t)kGemmStages * kGemmStageDoubles * sizeof(double);
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem)
@@ -343,88 +350,106 @@ __device__ __forceinline__ void dmma_884(double& d0, double& d1, double a, doubl
                : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(kGemmThreads) gemm_sub_kernel(double* __restrict__ C, int ldc,
-                                                                const double* __restrict__ A, int lda,
-                                                                const double* __restrict__ B, int ldb, int M,
-                                                                int Nc, int K) {
+__global__ void __launch_bounds__(kGemmThreads, 2) gemm_sub_kernel(double* __restrict__ C, int ldc,
+                                                                   const double* __restrict__ A, int lda,
+                                                                   const double* __restrict__ B, int ldb, int M,
+                                                                   int Nc, int K) {
   extern __shared__ __align__(16) double gsm[];
-  auto sA = [&](int buf) { return gsm + buf * (kGemmBM * kGemmLdA); };
-  auto sB = [&](int buf) { return gsm + 2 * kGemmBM * kGemmLdA + buf * (kGemmBK * kGemmLdB); };
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp >> 1, wn = warp & 1;  // 4 x 2 warps, warp tile 32 x 64
+  const int wm = warp >> 1, wn = warp & 1;  // 4 x 2 warps, warp tile 32 x 32
   const int m0 = blockIdx.y * kGemmBM, n0 = blockIdx.x * kGemmBN;
   const int gid = lane >> 2, tig = lane & 3;
 
-  auto load_tiles = [&](int buf, int k0) {
+  auto load_tiles = [&](int stage, int k0) {
+    double* sA = gsm + stage * kGemmStageDoubles;
+    double* sB = sA + kGemmBM * kGemmLdA;
     // A tile: 128 rows x 16 k = 128 x 8 chunks of 16 B; rows clamped (results of clamped rows are discarded)
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
       const int e = tid + it * kGemmThreads;
       const int r = e >> 3, ch = e & 7;
       const int gr = min(m0 + r, M - 1);
-      cp_async16(sA(buf) + r * kGemmLdA + ch * 2, A + (size_t)gr * lda + k0 + ch * 2);
+      cp_async16(sA + r * kGemmLdA + ch * 2, A + (size_t)gr * lda + k0 + ch * 2);
     }
-    // B tile: 16 k x 128 columns = 16 x 64 chunks; columns past Nc read in-allocation padding (discarded)
+    // B tile: 16 k x 64 columns = 16 x 32 chunks; columns past Nc are clamped into the row (results discarded)
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
+    for (int it = 0; it < 2; ++it) {
       const int e = tid + it * kGemmThreads;
-      const int r = e >> 6, ch = e & 63;
+      const int r = e >> 5, ch = e & 31;
       int gc = n0 + ch * 2;
-      if (gc >= Nc) gc = (Nc - 1) & ~1;  // keep the address inside the row
-      cp_async16(sB(buf) + r * kGemmLdB + ch * 2, B + (size_t)(k0 + r) * ldb + gc);
+      if (gc >= Nc) gc = (Nc - 1) & ~1;
+      cp_async16(sB + r * kGemmLdB + ch * 2, B + (size_t)(k0 + r) * ldb + gc);
     }
-    cp_async_commit();
   };
 
-  double acc[4][8][2];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
   const int nk = K / kGemmBK;
-  load_tiles(0, 0);
-  for (int kt = 0; kt < nk; ++kt) {
-    const int buf = kt & 1;
-    if (kt + 1 < nk) {
-      load_tiles(buf ^ 1, (kt + 1) * kGemmBK);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
+#pragma unroll
+  for (int s = 0; s < kGemmStages - 1; ++s) {
+    if (s < nk) load_tiles(s, s * kGemmBK);
+    cp_async_commit();
+  }
+
+  // acc <- C (thread holds C[row = gid][col = 2*tig, 2*tig+1] of each 8x8 tile); out-of-range entries are never stored
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = m0 + wm * 32 + i * 8 + gid;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = n0 + wn * 32 + j * 8 + tig * 2;
+      acc[i][j][0] = acc[i][j][1] = 0.0;
+      if (r < M) {
+        const double* cp = C + (size_t)r * ldc + c;
+        if (c + 1 < Nc) {
+          const double2 v = *reinterpret_cast<const double2*>(cp);
+          acc[i][j][0] = v.x;
+          acc[i][j][1] = v.y;
+        } else if (c < Nc) {
+          acc[i][j][0] = cp[0];
+        }
+      }
     }
-    __syncthreads();
-    const double* pa = sA(buf) + (wm * 32 + gid) * kGemmLdA + tig;
-    const double* pb = sB(buf) + tig * kGemmLdB + wn * 64 + gid;
+  }
+
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_async_wait<kGemmStages - 2>();  // this thread's copies of tile kt have landed
+    __syncthreads();                   // ... everyone's have, and everyone is done with the stage refilled below
+    {
+      const int nxt = kt + kGemmStages - 1;
+      if (nxt < nk) load_tiles(nxt % kGemmStages, nxt * kGemmBK);
+      cp_async_commit();
+    }
+    const double* sA = gsm + (kt % kGemmStages) * kGemmStageDoubles;
+    const double* sB = sA + kGemmBM * kGemmLdA;
+    const double* pa = sA + (wm * 32 + gid) * kGemmLdA + tig;
+    const double* pb = sB + tig * kGemmLdB + wn * 32 + gid;
 #pragma unroll
     for (int ks = 0; ks < kGemmBK; ks += 4) {
-      double af[4], bf[8];
+      double af[4], bf[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) af[i] = pa[i * 8 * kGemmLdA + ks];
+      for (int i = 0; i < 4; ++i) af[i] = -pa[i * 8 * kGemmLdA + ks];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) bf[j] = pb[ks * kGemmLdB + j * 8];
+      for (int j = 0; j < 4; ++j) bf[j] = pb[ks * kGemmLdB + j * 8];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dmma_884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        for (int j = 0; j < 4; ++j) dmma_884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
     }
-    __syncthreads();
   }
-  // C -= acc  (thread holds C[row = gid][col = 2*tig, 2*tig+1] of each 8x8 tile)
+  cp_async_wait<0>();
+
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int r = m0 + wm * 32 + i * 8 + gid;
     if (r >= M) continue;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = n0 + wn * 64 + j * 8 + tig * 2;
+    for (int j = 0; j < 4; ++j) {
+      const int c = n0 + wn * 32 + j * 8 + tig * 2;
       double* cp = C + (size_t)r * ldc + c;
       if (c + 1 < Nc) {
-        double2 v = *reinterpret_cast<double2*>(cp);
-        v.x -= acc[i][j][0];
-        v.y -= acc[i][j][1];
-        *reinterpret_cast<double2*>(cp) = v;
+        *reinterpret_cast<double2*>(cp) = make_double2(acc[i][j][0], acc[i][j][1]);
       } else if (c < Nc) {
-        cp[0] -= acc[i][j][0];
+        cp[0] = acc[i][j][0];
       }
     }
   }
@@ -541,6 +566,8 @@ static int gemm_sub(b200rbf_ctx* h, double* C, int ldc, const double* A, int lda
   static bool attr = false;
   if (!attr) {
     B2_CUDA(cudaFuncSetAttribute(gemm_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+    B2_CUDA(cudaFuncSetAttribute(gemm_sub_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 (int)cudaSharedmemCarveoutMaxShared));
     attr = true;
   }
   dim3 grid((Nc + kGemmBN - 1) / kGemmBN, (M + kGemmBM - 1) / kGemmBM);
@@ -576,7 +603,8 @@ int lu_factor_device(b200rbf_ctx* h, double* A, int ld, int N, int rcol0, int nc
     attr = true;
   }
 
-  for (int j0 = 0; j0 < N; j0 += NB) {
+  // factor the panel starting at column j0 on `stream`
+  auto launch_panel = [&](int j0, cudaStream_t stream) -> int {
     const int nb = (N - j0 < NB) ? (N - j0) : NB;
     const int prow = N - j0;
     const int st = nb | 1;
@@ -596,36 +624,65 @@ int lu_factor_device(b200rbf_ctx* h, double* A, int ld, int N, int rcol0, int nc
     pa.barrier = barrier; pa.bar_base = bar_base; pa.info = info_dev;
     const size_t smem = ((size_t)R * st + nb) * sizeof(double);
     void* kargs[] = {&pa};
-    B2_CUDA(cudaLaunchCooperativeKernel((void*)panel_kernel, dim3(G), dim3(kPanelThreads), kargs, smem, h->stream));
+    B2_CUDA(cudaLaunchCooperativeKernel((void*)panel_kernel, dim3(G), dim3(kPanelThreads), kargs, smem, stream));
     h->launches++;
     bar_base += (unsigned long long)nb * G;
+    return 0;
+  };
+  // apply the factored panel (j0, nb) to columns [ca, cb): U12 = L11^-1 A12 in 32-row steps, then A22 -= L21 U12
+  auto update_cols = [&](int j0, int nb, int ca, int cb) -> int {
+    if (ca >= cb) return 0;
+    for (int s0 = 0; s0 < nb; s0 += 32) {
+      const int rows = (nb - s0 < 32) ? (nb - s0) : 32;
+      trsm32_kernel<<<(cb - ca + 127) / 128, 128, 0, h->stream>>>(A, ld, j0 + s0, rows, ca, cb);
+      h->launches++;
+      B2_CUDA(cudaGetLastError());
+      const int below = nb - (s0 + rows);
+      if (below > 0) {
+        // rows [j0+s0+rows, j0+nb) of A12 -= L11[those rows, s0 .. s0+rows) * X[s0 .. s0+rows)   (rows == 32 here)
+        B2_TRY(gemm_sub(h, A + (size_t)(j0 + s0 + rows) * ld + ca, ld, A + (size_t)(j0 + s0 + rows) * ld + j0 + s0, ld,
+                        A + (size_t)(j0 + s0) * ld + ca, ld, below, cb - ca, rows));
+      }
+    }
+    const int c0 = j0 + nb;
+    if (c0 < N) {  // trailing rows
+      B2_TRY(gemm_sub(h, A + (size_t)c0 * ld + ca, ld, A + (size_t)c0 * ld + j0, ld, A + (size_t)j0 * ld + ca, ld,
+                      N - c0, cb - ca, nb));
+    }
+    return 0;
+  };
 
-    const int other = ncols - nb;
-    if (other > 0) {
-      laswp_kernel<<<(other + 255) / 256, 256, 0, h->stream>>>(A, ld, j0, nb, ncols, ipiv);
+  const bool lookahead = h->lu_lookahead && h->la_stream != nullptr;
+  B2_TRY(launch_panel(0, h->stream));
+  for (int j0 = 0; j0 < N; j0 += NB) {
+    const int nb = (N - j0 < NB) ? (N - j0) : NB;
+    // row interchanges of this panel on every column outside it (the panel itself was swapped in shared memory)
+    if (ncols - nb > 0) {
+      laswp_kernel<<<(ncols - nb + 255) / 256, 256, 0, h->stream>>>(A, ld, j0, nb, ncols, ipiv);
       h->launches++;
       B2_CUDA(cudaGetLastError());
     }
-    const int c0 = (j0 + nb < N) ? j0 + nb : rcol0;  // non-final panels have even nb; the final one jumps the gap
-    if (c0 < ncols) {
-      // U12 = L11^-1 A12 in 32-row steps
-      for (int s0 = 0; s0 < nb; s0 += 32) {
-        const int rows = (nb - s0 < 32) ? (nb - s0) : 32;
-        trsm32_kernel<<<(ncols - c0 + 127) / 128, 128, 0, h->stream>>>(A, ld, j0 + s0, rows, c0, ncols);
-        h->launches++;
-        B2_CUDA(cudaGetLastError());
-        const int below = nb - (s0 + rows);
-        if (below > 0) {
-          // rows [j0+s0+rows, j0+nb) of A12 -= L11[those rows, s0 .. s0+rows) * X[s0 .. s0+rows)   (rows == 32 here)
-          B2_TRY(gemm_sub(h, A + (size_t)(j0 + s0 + rows) * ld + c0, ld, A + (size_t)(j0 + s0 + rows) * ld + j0 + s0,
-                          ld, A + (size_t)(j0 + s0) * ld + c0, ld, below, ncols - c0, rows));
-        }
-      }
-      // trailing update A22 -= L21 U12  (includes the right-hand-side columns)
-      if (c0 < N) {
-        B2_TRY(gemm_sub(h, A + (size_t)c0 * ld + c0, ld, A + (size_t)c0 * ld + j0, ld, A + (size_t)j0 * ld + c0, ld,
-                        N - c0, ncols - c0, nb));
-      }
+    const int c0 = j0 + nb;
+    if (c0 >= N) {  // final panel: only the right-hand-side columns remain (they start at the even column rcol0)
+      B2_TRY(update_cols(j0, nb, rcol0, ncols));
+      break;
+    }
+    // non-final panels have nb == NB (even), so c0 and c0 + nb1 below are 16-byte aligned columns
+    const int nb1 = (N - c0 < NB) ? (N - c0) : NB;
+    const int rest = (c0 + nb1 < N) ? c0 + nb1 : rcol0;
+    B2_TRY(update_cols(j0, nb, c0, c0 + nb1));  // the next panel's columns first
+    if (lookahead) {
+      // panel k+1 touches only A[c0:, c0:c0+nb1), ipiv[c0:c0+nb1) and the mailbox: disjoint from what the rest of
+      // update k reads (L21, U12 right of c0+nb1) and writes (columns >= c0+nb1)
+      B2_CUDA(cudaEventRecord(h->ev_la1, h->stream));
+      B2_CUDA(cudaStreamWaitEvent(h->la_stream, h->ev_la1, 0));
+      B2_TRY(launch_panel(c0, h->la_stream));
+      B2_CUDA(cudaEventRecord(h->ev_la2, h->la_stream));
+      B2_TRY(update_cols(j0, nb, rest, ncols));
+      B2_CUDA(cudaStreamWaitEvent(h->stream, h->ev_la2, 0));
+    } else {
+      B2_TRY(update_cols(j0, nb, rest, ncols));
+      B2_TRY(launch_panel(c0, h->stream));
     }
   }
   return 0;

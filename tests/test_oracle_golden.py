@@ -125,3 +125,15 @@ def test_oracle_matches_live_reference():
     q = lb + (ub - lb) * rng.random((33, d))
     assert np.array_equal(r.predict(q), o.predict(q))
     assert np.array_equal(r.predict_deriv(q), o.predict_deriv(q))
+
+
+def test_strategy_trace_replay_with_the_oracle():
+    """The recorded reference proposals (config #1 in full, the first calls of #2 and #5) are reproduced by the
+    oracle under teacher-forced replay -- this also pins the replay logic the GPU test relies on."""
+    from trace_replay import OracleBackend, replay
+
+    ncalls, mismatches, ties, _, _ = replay("trace_dycors.npz", OracleBackend())
+    assert ncalls > 400 and not mismatches and ties == 0
+    for fname in ("trace_srbf.npz", "trace_sop.npz"):
+        ncalls, mismatches, ties, wp, wd = replay(fname, OracleBackend(), max_calls=60)
+        assert ncalls == 60 and not mismatches and ties == 0 and wp < 1e-12 and wd < 1e-12

@@ -1,0 +1,83 @@
+"""Teacher-forced replay of the strategy traces written by tools/make_strategy_traces.py (shared by the CPU oracle
+test and the GPU parity test)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, Problem, relmax
+
+
+class GpuBackend:
+    def __init__(self):
+        import pysot_b200 as pb
+
+        self.pb = pb
+        self.candidate_dycors, self.candidate_srbf = pb.candidate_dycors, pb.candidate_srbf
+
+    def surrogate(self, d, lb, ub):
+        return self.pb.GpuRBFInterpolant(dim=d, lb=lb, ub=ub, kernel=self.pb.CubicKernel(), tail=self.pb.LinearTail(d))
+
+
+class OracleBackend:
+    def __init__(self):
+        from oracle import rbf_oracle as orc
+
+        self.orc = orc
+        self.candidate_dycors, self.candidate_srbf = orc.candidate_dycors, orc.candidate_srbf
+
+    def surrogate(self, d, lb, ub):
+        return self.orc.OracleRBF(d, lb, ub, "cubic", "linear")
+
+
+def replay(fname, backend, max_calls=None):
+    path = os.path.join(GOLDEN, fname)
+    if not os.path.exists(path):
+        pytest.skip("%s not generated" % fname)
+    g = np.load(path)
+    d = int(g["dim"])
+    prob = Problem(g["lb"], g["ub"], g["int_var"])
+    kind = str(g["kind"])
+    states = {int(c): i for i, c in enumerate(g["state_call"])}
+    s = backend.surrogate(d, prob.lb, prob.ub)
+    ncalls = len(g["n"]) if max_calls is None else min(max_calls, len(g["n"]))
+    seg, have = -1, 0
+    pend_off = np.concatenate(([0], np.cumsum(g["pend_cnt"])))
+    pt_off = np.concatenate(([0], np.cumsum(g["num_pts"])))
+    mismatches, ties, worst_deriv, worst_pred = [], 0, 0.0, 0.0
+    for i in range(ncalls):
+        if int(g["seg"][i]) != seg:  # restart: the strategy reset the surrogate (surrogate_strategy.py:228)
+            s.reset()
+            seg, have = int(g["seg"][i]), 0
+        n = int(g["n"][i])
+        if n > have:
+            s.add_points(g["allX"][seg + have:seg + n], g["allfX"][seg + have:seg + n])
+            have = n
+        X, fX = g["allX"][seg:seg + n], g["allfX"][seg:seg + n]
+        Xpend = g["pend"][pend_off[i]:pend_off[i + 1]]
+        p = int(g["num_pts"][i])
+        w = list(g["weights"][pt_off[i]:pt_off[i + 1]])
+        if i in states:
+            k = states[i]
+            np.random.set_state(("MT19937", g["state_key"][k], int(g["state_pos"][k]), int(g["state_gauss"][k]),
+                                 float(g["state_cached"][k])))
+        if kind == "dycors":
+            xb = g["xbest"][i]
+            pts = backend.candidate_dycors(num_pts=p, opt_prob=prob, surrogate=s, X=X, fX=fX, weights=w,
+                                      prob_perturb=float(g["prob_perturb"][i]), Xpend=Xpend,
+                                      sampling_radius=float(g["sampling_radius"][i]), num_cand=int(g["num_cand"][i]),
+                                      xbest=None if np.isnan(xb[0]) else xb.copy())
+        else:
+            pts = backend.candidate_srbf(num_pts=p, opt_prob=prob, surrogate=s, X=X, fX=fX, weights=w, Xpend=Xpend,
+                                    sampling_radius=float(g["sampling_radius"][i]), num_cand=int(g["num_cand"][i]))
+        ref = g["new_points"][pt_off[i]:pt_off[i + 1]]
+        if not np.array_equal(pts, ref):
+            first = int(np.argmax(np.any(pts != ref, axis=1)))
+            if g["margins"][pt_off[i] + first] <= 1e-12:
+                ties += 1
+            else:
+                mismatches.append((i, first, float(g["margins"][pt_off[i] + first])))
+        if "deriv" in g.files:  # config #5 add-on: gradient at every proposed point
+            worst_deriv = max(worst_deriv, relmax(s.predict_deriv(ref), g["deriv"][pt_off[i]:pt_off[i + 1]]))
+            worst_pred = max(worst_pred, relmax(s.predict(ref), g["pred"][pt_off[i]:pt_off[i + 1]]))
+    return ncalls, mismatches, ties, worst_pred, worst_deriv

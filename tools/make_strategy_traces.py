@@ -16,8 +16,9 @@ test can tell a legitimate tie (<= 1e-12, north_star) from a wrong answer.
 Configs (BASELINE.json):
   #1 DYCORSStrategy, Ackley 10-D, cubic + linear tail, SLHD 2(d+1), 500 evals, SerialController
   #2 SRBFStrategy, Levy 30-D, 8 asynchronous workers (deterministic emulation), 100*dim candidates, 2000 evals
-  #5 SOPStrategy, Rastrigin 20-D, 8 centers, predict_deriv at every proposed point; 600 evals here (the
-     reference's pure-Python nd_sorting makes 3000 evals a multi-hour run)
+  #5 SOPStrategy, Rastrigin 20-D, 8 centers, 8 asynchronous workers (proposals are only requested while a worker is free,
+     see tools/poap_standin.py), predict_deriv at every proposed point; 600 evals here
+     (the reference's pure-Python nd_sorting makes 3000 evals a multi-hour run)
 """
 import os
 import sys

@@ -158,6 +158,13 @@ class SimAsyncController(Controller):
 
     def run(self):
         while True:
+            # Ask for a proposal only while a worker is free.  pySOT's asynchronous strategies DROP a rejected
+            # adaptive proposal (surrogate_strategy.py:399-406) and SOPStrategy then leaks the center it was
+            # generated from (sop_strategy.py:257-262) until generate_evals raises IndexError, so a controller that
+            # proposed with all workers busy would break the reference itself.
+            if len(self.running) >= self.workers:
+                self._complete_oldest()
+                continue
             p = self.strategy.propose_action()
             if p is None:
                 if not self.running:
