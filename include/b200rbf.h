@@ -50,7 +50,13 @@ enum {
   /* LU panel width (default 128; multiple of 32)                                                       */
   B200RBF_OPT_LU_PANEL = 3,
   /* 1 (default): factor panel k+1 on a second, high-priority stream while the rest of trailing update k runs  */
-  B200RBF_OPT_LU_LOOKAHEAD = 4
+  B200RBF_OPT_LU_LOOKAHEAD = 4,
+  /* cp.async ring depth of the DMMA GEMM: 2, 3, or 0 = auto (2 while a look-ahead panel shares the SMs, else 3) */
+  B200RBF_OPT_GEMM_STAGES = 5,
+  /* 1 (default): surrogate values use the norm expansion |u|^2 + |c|^2 - 2 u.c with the dot products on the FP64
+   *    tensor path and a direct recomputation of near pairs (score_mma.cuh; ~1.6x fewer FP64 cycles at d = 50,
+   *    relative error of r^2 <= ~1e-12).  0: direct differences everywhere.  Ignored when EXACT_DIST is set.     */
+  B200RBF_OPT_MMA_DIST = 6
 };
 
 const char* b200rbf_last_error(void);

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libb200rbf.so")
 
 KERNEL_CUBIC, KERNEL_TPS, KERNEL_LINEAR = 0, 1, 2
 TAIL_LINEAR, TAIL_CONSTANT = 0, 1
-OPT_EXACT_DIST, OPT_CHUNK_ROWS, OPT_LU_PANEL, OPT_LU_LOOKAHEAD = 1, 2, 3, 4
+OPT_EXACT_DIST, OPT_CHUNK_ROWS, OPT_LU_PANEL, OPT_LU_LOOKAHEAD, OPT_GEMM_STAGES, OPT_MMA_DIST = 1, 2, 3, 4, 5, 6
 E_INVAL, E_CUDA, E_STATE, E_SINGULAR, E_NOMEM = -1, -2, -3, -4, -5
 
 _dp = C.POINTER(C.c_double)

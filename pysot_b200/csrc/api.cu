@@ -1,7 +1,7 @@
 // C ABI of libb200rbf.so (include/b200rbf.h): argument checking, host<->device staging, stream ordering.
 #include <stdarg.h>
 
-#include "score_kernels.cuh"
+#include "score_mma.cuh"
 
 namespace b200rbf {
 
@@ -62,6 +62,20 @@ __global__ void split_coef_kernel(const double* __restrict__ c, int t, int n, do
   if (i < npad) coef[i] = i < n ? c[t + i] : 0.0;
   if (i < t) tailc[i] = c[i];
 }
+// shifted (u - 0.5) centers with row stride ds and their squared norms (operands of score_mma_kernel)
+__global__ void mma_points_kernel(const double* __restrict__ src, int n, int d, double* __restrict__ dst, int npad,
+                                  int ds, double* __restrict__ cnorm) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npad) return;
+  const int si = i < n ? i : n - 1;
+  double n2 = 0.0;
+  for (int k = 0; k < ds; ++k) {
+    const double v = k < d ? src[(size_t)si * d + k] - 0.5 : 0.0;
+    dst[(size_t)i * ds + k] = v;
+    n2 = fma(v, v, n2);
+  }
+  cnorm[i] = n2;
+}
 __global__ void negate_stats_kernel(const double* __restrict__ s, double* __restrict__ out) {
   if (threadIdx.x == 0) {
     out[0] = s[0];
@@ -107,6 +121,15 @@ int install_model(b200rbf_ctx* h, const double* Xu_dev, const double* c_dev, int
                                                               M.tailc.as<double>());
   h->launches++;
   B2_CUDA(cudaGetLastError());
+  if (M.dpad <= kMaxRegDim) {  // operands of the DMMA score kernel
+    M.ds = mma_stride(d);
+    B2_TRY(M.centers_x.reserve((size_t)M.npad * M.ds * sizeof(double)));
+    B2_TRY(M.cnorm.reserve((size_t)M.npad * sizeof(double)));
+    mma_points_kernel<<<(M.npad + 127) / 128, 128, 0, h->stream>>>(Xu_dev, n, d, M.centers_x.as<double>(), M.npad, M.ds,
+                                                                  M.cnorm.as<double>());
+    h->launches++;
+    B2_CUDA(cudaGetLastError());
+  }
   M.loaded = true;
   h->score.valid = false;
   return 0;
@@ -145,7 +168,30 @@ struct ScorePlan {
 // candidates per CTA of the kernel that serves this padded dimension
 int block_rows(int dpad) { return dpad <= kMaxRegDim ? kScoreThreads : score_generic_threads(); }
 
+bool use_mma(const b200rbf_ctx* h, bool with_phi) {
+  return with_phi && h->mma_dist && !h->exact_dist && h->model.dpad <= kMaxRegDim;
+}
+
+int launch_score_mma(b200rbf_ctx* h, const ScoreArgs& a) {
+  const Model& M = h->model;
+  MmaArgs ma;
+  ma.s = a;
+  ma.s.pts = M.centers_x.as<double>();
+  ma.cnorm = M.cnorm.as<double>();
+  ma.ds = M.ds;
+  const int k4 = (M.d + 3) / 4;
+  switch ((k4 - 1) / 4) {
+    case 0: return launch_score_mma_group0(h, ma, k4, M.kernel);
+    case 1: return launch_score_mma_group1(h, ma, k4, M.kernel);
+    case 2: return launch_score_mma_group2(h, ma, k4, M.kernel);
+    case 3: return launch_score_mma_group3(h, ma, k4, M.kernel);
+  }
+  set_error("internal: no DMMA score kernel for d = %d", M.d);
+  return B200RBF_EINVAL;
+}
+
 int launch_score_any(b200rbf_ctx* h, const ScoreArgs& a, int dpad, int kernel, bool exact, bool with_phi) {
+  if (use_mma(h, with_phi)) return launch_score_mma(h, a);
   if (dpad > kMaxRegDim) return launch_score_generic(h, a, dpad, kernel, exact, with_phi);
   switch ((dpad - 2) / 8) {
     case 0: return launch_score_group0(h, a, dpad, kernel, exact, with_phi);
@@ -207,7 +253,7 @@ int score_rows(b200rbf_ctx* h, const ScorePlan& plan, const double* cand_dev, lo
 // H2D copy of chunk i+1 overlaps the kernels of chunk i.  dst_dev receives the rows when they come from the host.
 int score_pipeline(b200rbf_ctx* h, const ScorePlan& plan, const double* cand, long long m, double* dst_dev,
                    const double* box, double* fvals, double* dmerit, double* parts, int nparts,
-                   const double** cand_dev_out) {
+                   const double** cand_dev_out, int* parts_used) {
   const Model& M = h->model;
   const PtrKind kind = ptr_kind(cand);
   if (kind == kDevice) {
@@ -215,9 +261,23 @@ int score_pipeline(b200rbf_ctx* h, const ScorePlan& plan, const double* cand, lo
     B2_CHECK(m <= kMaxRows, B200RBF_EINVAL, "too many candidates");
     B2_TRY(score_rows(h, plan, cand, 0, m, box, fvals, dmerit, parts, nparts, 0));
     *cand_dev_out = cand;
+    *parts_used = (int)((m + block_rows(M.dpad) - 1) / block_rows(M.dpad));
     return 0;
   }
-  const long long chunk = h->chunk_rows;
+  // chunk = a whole number of full waves of the score kernel (resident CTAs x candidates per CTA): consecutive
+  // chunk kernels run back to back on one stream, so a chunk that ends in a mostly empty wave wastes the GPU
+  long long chunk = h->chunk_rows;
+  {
+    ScoreArgs q;
+    memset(&q, 0, sizeof(q));
+    int occ = 0;
+    q.occ_out = &occ;
+    B2_TRY(launch_score_any(h, q, M.dpad, M.kernel, h->exact_dist, plan.with_phi));
+    const long long wave = (long long)h->sm_count * (occ > 0 ? occ : 1) * block_rows(M.dpad);
+    long long waves = (chunk + wave / 2) / wave;
+    if (waves < 1) waves = 1;
+    chunk = waves * wave;
+  }
   const size_t row_bytes = (size_t)M.d * sizeof(double);
   if (kind == kPageable) {
     const long long cr = m < chunk ? m : chunk;
@@ -243,17 +303,16 @@ int score_pipeline(b200rbf_ctx* h, const ScorePlan& plan, const double* cand, lo
     part_off += (int)((rows + block_rows(M.dpad) - 1) / block_rows(M.dpad));
   }
   *cand_dev_out = dst_dev;
+  *parts_used = part_off;
   return 0;
 }
 
 int count_parts(long long m, long long chunk, bool chunked, int br) {
-  if (!chunked) return (int)((m + br - 1) / br);
-  long long total = 0;
-  for (long long r0 = 0; r0 < m; r0 += chunk) {
-    const long long rows = (m - r0 < chunk) ? (m - r0) : chunk;
-    total += (rows + br - 1) / br;
-  }
-  return (int)total;
+  // upper bound on the per-CTA partial slots: one launch per chunk, each rounds its row count up to whole CTAs
+  // (the pipeline may round `chunk` up to whole waves, which only lowers the number of launches)
+  (void)chunk;
+  (void)chunked;
+  return (int)((m + br - 1) / br) + 4096;
 }
 
 }  // namespace
@@ -313,6 +372,7 @@ int b200rbf_destroy(b200rbf_handle h) {
   cudaStreamSynchronize(h->copy_stream);
   Model& M = h->model;
   M.centers.release(); M.centersT.release(); M.coef.release(); M.tailc.release();
+  M.centers_x.release(); M.cnorm.release();
   ScoreState& S = h->score;
   S.cand_own.release(); S.fvals.release(); S.dmerit.release(); S.parts.release(); S.pair_parts.release();
   S.stats.release(); S.winner.release(); S.results.release(); S.dist.release(); S.box.release();
@@ -342,11 +402,17 @@ int b200rbf_set_option(b200rbf_handle h, int option, long long value) {
   B2_CHECK(h != nullptr, B200RBF_EINVAL, "handle is NULL");
   switch (option) {
     case B200RBF_OPT_EXACT_DIST: h->exact_dist = value != 0; return 0;
+    case B200RBF_OPT_MMA_DIST: h->mma_dist = value != 0; return 0;
     case B200RBF_OPT_CHUNK_ROWS:
       B2_CHECK(value >= 256, B200RBF_EINVAL, "chunk rows must be >= 256");
       h->chunk_rows = value;
       return 0;
     case B200RBF_OPT_LU_LOOKAHEAD: h->lu_lookahead = value != 0; return 0;
+    case B200RBF_OPT_GEMM_STAGES:
+      B2_CHECK(value == 0 || value == 2 || value == 3, B200RBF_EINVAL, "GEMM stages must be 0 (auto), 2 or 3");
+      h->gemm_stages_auto = value == 0;
+      h->gemm_stages = value == 0 ? 3 : (int)value;
+      return 0;
     case B200RBF_OPT_LU_PANEL:
       B2_CHECK(value >= 32 && value <= 128 && value % 32 == 0, B200RBF_EINVAL, "LU panel must be 32, 64, 96 or 128");
       h->lu_panel = (int)value;
@@ -434,7 +500,8 @@ int b200rbf_predict(b200rbf_handle h, const double* x, long long m, const double
   }
   ScorePlan plan;
   const double* used = nullptr;
-  B2_TRY(score_pipeline(h, plan, x, m, xdev, h->tmp_box.as<double>(), fv, nullptr, parts, nparts, &used));
+  int parts_used = 0;
+  B2_TRY(score_pipeline(h, plan, x, m, xdev, h->tmp_box.as<double>(), fv, nullptr, parts, nparts, &used, &parts_used));
   if (host_out) B2_TRY(copy_out(h, out, fv, (size_t)m * sizeof(double)));
   B2_CUDA(cudaStreamSynchronize(h->stream));
   return 0;
@@ -518,11 +585,12 @@ int b200rbf_score(b200rbf_handle h, const double* cand, long long m, const doubl
     B2_TRY(S.cand_own.reserve((size_t)m * M.d * sizeof(double)));
     own = S.cand_own.as<double>();
   }
+  int parts_used = 0;
   B2_CUDA(cudaEventRecord(h->ev_s0, h->stream));
   B2_TRY(score_pipeline(h, plan, cand, m, own, S.box.as<double>(), S.fvals.as<double>(), S.dmerit.as<double>(),
-                        S.parts.as<double>(), S.nparts, &S.cand));
+                        S.parts.as<double>(), S.nparts, &S.cand, &parts_used));
   B2_CUDA(cudaEventRecord(h->ev_s1, h->stream));
-  B2_TRY(launch_stats(h, S.parts.as<double>(), S.nparts, nparts, 3, S.stats.as<double>()));
+  B2_TRY(launch_stats(h, S.parts.as<double>(), S.nparts, parts_used, 3, S.stats.as<double>()));
   S.m = m;
   S.d = M.d;
   if (fvals_out) B2_TRY(copy_out(h, fvals_out, S.fvals.p, (size_t)m * sizeof(double)));

@@ -117,7 +117,12 @@ constexpr int kJT = B2_JT;                      // centers processed together pe
 constexpr int kGenMaxDim = 192;                 // largest padded dimension of the shared-memory (generic) score kernel
 
 inline int pad_dim(int d) { return (d + 1) & ~1; }                       // even: rows are multiples of 16 B
-inline int pad_rows(int n) { return ((n + kJT - 1) / kJT) * kJT; }       // multiples of kJT (duplicates of last row)
+inline int pad_rows(int n) { return (n + 15) & ~15; }                    // multiples of 16 (duplicates of last row)
+inline int mma_stride(int d) {                                            // center row stride of the DMMA kernel:
+  int s = (d + 3) & ~3;                                                   // >= 4 ceil(d/4), == 4 (mod 16) doubles so the
+  while ((s & 15) != 4) s += 4;                                           // B-fragment LDS.64 are bank-conflict free
+  return s;
+}
 
 // ---------------------------------------------------------------- the handle
 struct Model {
@@ -128,6 +133,9 @@ struct Model {
   DevBuf coef;      // npad RBF weights (pad = 0)
   DevBuf tailc;     // ntail tail coefficients (lambda_0, lambda_1..d)
   int npadT = 0;
+  // operands of the DMMA score kernel (score_mma.cuh): centers shifted by 0.5, row stride ds, and their squared norms
+  DevBuf centers_x, cnorm;
+  int ds = 0;
 };
 
 struct ScoreState {
@@ -168,11 +176,14 @@ struct b200rbf_ctx {
   cudaStream_t la_stream = nullptr;
   cudaEvent_t ev_la1 = nullptr, ev_la2 = nullptr;
   bool lu_lookahead = true;
+  int gemm_stages = 3;          // cp.async ring depth of the DMMA GEMM
+  bool gemm_stages_auto = true; // drop to 2 while a look-ahead panel shares the SMs
   b200rbf::PinBuf stage[2];
   b200rbf::PinBuf pin_small;
   long long launches = 0;
   bool exact_dist = false;
-  long long chunk_rows = 65536;
+  bool mma_dist = true;  // norm-expansion distances on the FP64 tensor path (score_mma.cuh) unless exact_dist
+  long long chunk_rows = 131072;  // target rows per H2D chunk; rounded to whole waves of the score kernel
   int lu_panel = 128;
   b200rbf::Model model;
   b200rbf::ScoreState score;
@@ -201,6 +212,7 @@ struct ScoreArgs {
   double* parts;           // 4 x nparts partial stats
   int nparts;
   int part_off;            // first partial slot of this launch
+  int* occ_out;            // host only: non-null = do not launch, report resident CTAs per SM of the instantiation
 };
 
 // score kernel for kMaxRegDim < dpad <= kGenMaxDim (score_generic.cu) and its candidates-per-CTA

@@ -330,11 +330,11 @@ __global__ void __launch_bounds__(128) trsm32_kernel(double* __restrict__ A, int
 // Operands stream through a 3-stage cp.async ring with ONE barrier per k-step.  The C tile is loaded into the
 // accumulators up front (its latency hides behind the first k-steps) and A fragments are negated on the way in,
 // so acc = C - A B accumulates directly and the epilogue is store-only.
-constexpr int kGemmBM = 128, kGemmBN = 64, kGemmBK = 16, kGemmThreads = 256, kGemmStages = 3;
+constexpr int kGemmBM = 128, kGemmBN = 64, kGemmBK = 16, kGemmThreads = 256;
 constexpr int kGemmLdA = kGemmBK + 4;   // 20 doubles: 4 consecutive rows x 4 k hit 16 distinct bank pairs
 constexpr int kGemmLdB = kGemmBN + 4;   // 68 doubles (68 mod 16 == 4): same for 4 k x 4 columns
 constexpr int kGemmStageDoubles = kGemmBM * kGemmLdA + kGemmBK * kGemmLdB;
-constexpr size_t kGemmSmem = (size_t)kGemmStages * kGemmStageDoubles * sizeof(double);
+constexpr size_t gemm_smem_bytes(int stages) { return (size_t)stages * kGemmStageDoubles * sizeof(double); }
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem)
@@ -350,6 +350,7 @@ __device__ __forceinline__ void dmma_884(double& d0, double& d1, double a, doubl
                : "d"(a), "d"(b));
 }
 
+template <int kGemmStages>
 __global__ void __launch_bounds__(kGemmThreads, 2) gemm_sub_kernel(double* __restrict__ C, int ldc,
                                                                    const double* __restrict__ A, int lda,
                                                                    const double* __restrict__ B, int ldb, int M,
@@ -560,21 +561,30 @@ __global__ void __launch_bounds__(256) dmix_peak_kernel(double* out, int iters, 
 }  // namespace
 
 // =================================================================================================== host side
-static int gemm_sub(b200rbf_ctx* h, double* C, int ldc, const double* A, int lda, const double* B, int ldb, int M,
-                    int Nc, int K) {
-  if (M <= 0 || Nc <= 0 || K <= 0) return 0;
+template <int STAGES>
+static int gemm_sub_inst(b200rbf_ctx* h, double* C, int ldc, const double* A, int lda, const double* B, int ldb, int M,
+                         int Nc, int K) {
   static bool attr = false;
+  constexpr size_t smem = gemm_smem_bytes(STAGES);
   if (!attr) {
-    B2_CUDA(cudaFuncSetAttribute(gemm_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
-    B2_CUDA(cudaFuncSetAttribute(gemm_sub_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+    B2_CUDA(cudaFuncSetAttribute(gemm_sub_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2_CUDA(cudaFuncSetAttribute(gemm_sub_kernel<STAGES>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  (int)cudaSharedmemCarveoutMaxShared));
     attr = true;
   }
   dim3 grid((Nc + kGemmBN - 1) / kGemmBN, (M + kGemmBM - 1) / kGemmBM);
-  gemm_sub_kernel<<<grid, kGemmThreads, kGemmSmem, h->stream>>>(C, ldc, A, lda, B, ldb, M, Nc, K);
+  gemm_sub_kernel<STAGES><<<grid, kGemmThreads, smem, h->stream>>>(C, ldc, A, lda, B, ldb, M, Nc, K);
   h->launches++;
   B2_CUDA(cudaGetLastError());
   return 0;
+}
+
+static int gemm_sub(b200rbf_ctx* h, double* C, int ldc, const double* A, int lda, const double* B, int ldb, int M,
+                    int Nc, int K) {
+  if (M <= 0 || Nc <= 0 || K <= 0) return 0;
+  // 2 stages (58 KB) leave room for a look-ahead panel CTA beside one GEMM CTA on the same SM; 3 stages otherwise
+  return h->gemm_stages == 2 ? gemm_sub_inst<2>(h, C, ldc, A, lda, B, ldb, M, Nc, K)
+                             : gemm_sub_inst<3>(h, C, ldc, A, lda, B, ldb, M, Nc, K);
 }
 
 int lu_factor_device(b200rbf_ctx* h, double* A, int ld, int N, int rcol0, int ncols, int* ipiv, int* info_dev) {
@@ -623,8 +633,17 @@ int lu_factor_device(b200rbf_ctx* h, double* A, int ld, int N, int rcol0, int nc
     pa.mb_val = mb_val; pa.mb_row = mb_row; pa.mb_rows = mb_rows; pa.mb_diag = mb_diag; pa.nbmax = NB;
     pa.barrier = barrier; pa.bar_base = bar_base; pa.info = info_dev;
     const size_t smem = ((size_t)R * st + nb) * sizeof(double);
-    void* kargs[] = {&pa};
-    B2_CUDA(cudaLaunchCooperativeKernel((void*)panel_kernel, dim3(G), dim3(kPanelThreads), kargs, smem, stream));
+    if (stream == h->la_stream) {
+      // Look-ahead: a cooperative launch would wait for the whole GPU to drain, i.e. for the trailing update it is
+      // supposed to overlap.  A plain launch on the high-priority stream lets the panel's CTAs (at most one per SM)
+      // take SM slots as GEMM CTAs retire; the GEMM never waits on the panel, so every panel CTA becomes resident
+      // and the grid barrier completes.
+      panel_kernel<<<G, kPanelThreads, smem, stream>>>(pa);
+      B2_CUDA(cudaGetLastError());
+    } else {
+      void* kargs[] = {&pa};
+      B2_CUDA(cudaLaunchCooperativeKernel((void*)panel_kernel, dim3(G), dim3(kPanelThreads), kargs, smem, stream));
+    }
     h->launches++;
     bar_base += (unsigned long long)nb * G;
     return 0;
@@ -653,6 +672,8 @@ int lu_factor_device(b200rbf_ctx* h, double* A, int ld, int N, int rcol0, int nc
   };
 
   const bool lookahead = h->lu_lookahead && h->la_stream != nullptr;
+  const int saved_stages = h->gemm_stages;
+  if (lookahead && h->gemm_stages_auto) h->gemm_stages = 2;
   B2_TRY(launch_panel(0, h->stream));
   for (int j0 = 0; j0 < N; j0 += NB) {
     const int nb = (N - j0 < NB) ? (N - j0) : NB;
@@ -685,6 +706,7 @@ int lu_factor_device(b200rbf_ctx* h, double* A, int ld, int N, int rcol0, int nc
       B2_TRY(launch_panel(c0, h->stream));
     }
   }
+  h->gemm_stages = saved_stages;
   return 0;
 }
 

@@ -146,6 +146,10 @@ int launch_generic_inst(b200rbf_ctx* h, const ScoreArgs& a, int dpad) {
   const size_t smem = ((size_t)kGenStages * kGenTileRows * dpad + kGenStages * kGenTileRows + kGenStages +
                        4 * (kGenThreads / 32) + (size_t)dpad * kGenThreads) * 8;
   B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (a.occ_out != nullptr) {
+    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(a.occ_out, kern, kGenThreads, smem));
+    return 0;
+  }
   const long long blocks = (a.m + kGenThreads - 1) / kGenThreads;
   kern<<<(unsigned)blocks, kGenThreads, smem, h->stream>>>(a, dpad);
   h->launches++;

@@ -241,6 +241,10 @@ int launch_score_inst(b200rbf_ctx* h, const ScoreArgs& a) {
     B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
+  if (a.occ_out != nullptr) {  // query only: resident CTAs per SM of this instantiation
+    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(a.occ_out, kern, kScoreThreads, smem));
+    return 0;
+  }
   const long long blocks = (a.m + kScoreThreads - 1) / kScoreThreads;
   kern<<<(unsigned)blocks, kScoreThreads, smem, h->stream>>>(a);
   h->launches++;

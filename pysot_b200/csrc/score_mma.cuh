@@ -1,0 +1,274 @@
+// K2x: fused candidate x center kernel with the squared distance from the norm expansion
+//     r^2 = |u|^2 + |c|^2 - 2 u.c
+// where the dot products u.c run on the FP64 tensor path (mma.sync.m8n8k4.f64, SASS DMMA) and everything else
+// (r^2, sqrt, phi, weight FMA, running min) on the FP64 FMA pipe.  On sm_100 both share one datapath (DESIGN.md
+// section 4), so the gain over score_kernel is arithmetic, not an extra pipe: d FMA-equivalents per pair instead
+// of d subtractions + d FMAs (1.65x fewer FP64-pipe cycles at d = 50), with 15x fewer shared-memory loads because
+// the MMA reuses each center element across 32 candidates.
+//
+// Accuracy.  Coordinates are shifted by 0.5 (centre of the unit box) so |u|^2 + |c|^2 ~ d/6 instead of 2d/3.  The
+// expansion's absolute error in r^2 is ~ eps (|u|^2 + |c|^2); where that is not negligible relative to r^2 itself,
+// i.e. for NEAR pairs with r^2 < 2^-10 (|u|^2 + |c|^2), the pair is recomputed with direct differences (rare,
+// divergent slow path), so coincident points still give r = 0 exactly and `dmerit < dtol` (candidate_srbf.py:48)
+// is decided on a distance with full relative accuracy.  Elsewhere the relative error of r^2 is <= ~1e-12, far
+// inside the 1e-10 parity bar; `exact_dist` mode never uses this kernel.
+//
+// Work decomposition: one warp owns 32 candidates (4 m8 blocks).  Thread (gid = lane / 4, tig = lane % 4) holds
+// the A fragments u[gid + 8 i][4 k + tig] in registers for the whole kernel and receives, per 8-center block, the
+// dot products of candidates gid + 8 i with centers 2 tig, 2 tig + 1.  Per-candidate sums / minima are therefore
+// spread over the 4 threads of a quad and combined with two shuffles at the very end.  Center rows (stride ds == 4
+// mod 16 doubles: conflict-free B-fragment loads), their squared norms and weights arrive by TMA bulk copies.
+#pragma once
+#include "score_kernels.cuh"
+
+namespace b200rbf {
+
+constexpr int kMmaThreads = 128;  // 4 warps x 32 candidates
+constexpr int kMmaTileRows = 32;  // center rows per tile (two 16-center steps)
+constexpr int kMmaStages = 3;
+
+struct MmaArgs {
+  ScoreArgs s;          // pts = shifted centers (npad x ds), coef = weights, as in score_kernel
+  const double* cnorm;  // npad squared norms of the shifted centers
+  int ds;               // center row stride in doubles (== 4 mod 16, >= 4 * K4)
+};
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+// direct squared distance of candidate `row` to the shared-memory center row `cp` (slow path for near pairs)
+static __device__ __noinline__ double mma_exact_r2(const double* __restrict__ src, int d, const double* __restrict__ lb,
+                                            const double* __restrict__ range, const double* cp) {
+  double acc = 0.0;
+  for (int k = 0; k < d; ++k) {
+    double v = __ldg(src + k);
+    if (lb != nullptr) v = __ddiv_rn(__dsub_rn(v, __ldg(lb + k)), __ldg(range + k));
+    const double t = (v - 0.5) - cp[k];
+    acc = fma(t, t, acc);
+  }
+  return acc;
+}
+
+template <int K4, int KERN>
+__global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(MmaArgs ma) {
+  const ScoreArgs& a = ma.s;
+  const int ds = ma.ds;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* s_pts = reinterpret_cast<double*>(smem_raw);                    // [stages][rows * ds]
+  double* s_wts = s_pts + (size_t)kMmaStages * kMmaTileRows * ds;          // [stages][rows]
+  double* s_nrm = s_wts + kMmaStages * kMmaTileRows;                       // [stages][rows]
+  uint64_t* s_full = reinterpret_cast<uint64_t*>(s_nrm + kMmaStages * kMmaTileRows);
+  double* s_red = reinterpret_cast<double*>(s_full + kMmaStages);         // 4 x warps
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gid = lane >> 2, tig = lane & 3;
+  const long long base = ((long long)blockIdx.x * (kMmaThreads / 32) + warp) * 32;
+  const int ntiles = (a.npad + kMmaTileRows - 1) / kMmaTileRows;
+
+  if (tid == 0) {
+    for (int s = 0; s < kMmaStages; ++s) mbar_init(&s_full[s], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  auto issue = [&](int t) {
+    const int s = t % kMmaStages;
+    const int r0 = t * kMmaTileRows;
+    const int rows = min(kMmaTileRows, a.npad - r0);
+    mbar_expect_tx(&s_full[s], (uint32_t)rows * (uint32_t)(ds * 8 + 16));
+    tma_bulk_g2s(s_pts + (size_t)s * kMmaTileRows * ds, a.pts + (size_t)r0 * ds, (uint32_t)rows * ds * 8u, &s_full[s]);
+    tma_bulk_g2s(s_wts + s * kMmaTileRows, a.coef + r0, rows * 8u, &s_full[s]);
+    tma_bulk_g2s(s_nrm + s * kMmaTileRows, ma.cnorm + r0, rows * 8u, &s_full[s]);
+  };
+  if (tid == 0)
+    for (int t = 0; t < kMmaStages && t < ntiles; ++t) issue(t);
+
+  // A fragments: shifted unit-box coordinates of candidates base + gid + 8 i, dimensions 4 k + tig
+  double afr[4][K4];
+  double nx[4];
+  long long rows_i[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long row = base + gid + 8 * i;
+    rows_i[i] = row < a.m ? row : (a.m - 1);
+    const double* src = a.cand + rows_i[i] * (long long)a.d;
+    double n2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < K4; ++k) {
+      const int dim = 4 * k + tig;
+      double v = 0.0;
+      if (dim < a.d) {
+        v = __ldg(src + dim);
+        if (a.lb != nullptr) v = __ddiv_rn(__dsub_rn(v, __ldg(a.lb + dim)), __ldg(a.range + dim));
+        v -= 0.5;
+      }
+      afr[i][k] = v;
+      n2 = fma(v, v, n2);
+    }
+    n2 += __shfl_xor_sync(0xffffffffu, n2, 1);
+    n2 += __shfl_xor_sync(0xffffffffu, n2, 2);
+    nx[i] = n2;
+  }
+
+  double sum[4] = {0.0, 0.0, 0.0, 0.0};
+  const double inf = __longlong_as_double(0x7ff0000000000000LL);
+  double mn[4] = {inf, inf, inf, inf};
+  const double tau = 0.0009765625;  // 2^-10
+
+  for (int t = 0; t < ntiles; ++t) {
+    const int s = t % kMmaStages;
+    const int rows = min(kMmaTileRows, a.npad - t * kMmaTileRows);  // multiple of 16
+    mbar_wait(&s_full[s], (uint32_t)((t / kMmaStages) & 1));
+    const double* tp = s_pts + (size_t)s * kMmaTileRows * ds;
+    const double* tw = s_wts + s * kMmaTileRows;
+    const double* tn = s_nrm + s * kMmaTileRows;
+    for (int j0 = 0; j0 < rows; j0 += 16) {
+      double acc[4][2][2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jb = 0; jb < 2; ++jb) acc[i][jb][0] = acc[i][jb][1] = 0.0;
+      const double* pb = tp + (j0 + gid) * ds + tig;
+#pragma unroll
+      for (int k = 0; k < K4; ++k) {
+        const double b0 = pb[4 * k];
+        const double b1 = pb[8 * ds + 4 * k];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          dmma884(acc[i][0][0], acc[i][0][1], afr[i][k], b0);
+          dmma884(acc[i][1][0], acc[i][1][1], afr[i][k], b1);
+        }
+      }
+#pragma unroll
+      for (int jb = 0; jb < 2; ++jb) {
+        const int jc = j0 + 8 * jb + 2 * tig;
+        const double2 n2 = *reinterpret_cast<const double2*>(tn + jc);
+        const double2 w2 = *reinterpret_cast<const double2*>(tw + jc);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const double sq = nx[i] + (e ? n2.y : n2.x);
+            double r2 = fma(-2.0, acc[i][jb][e], sq);
+            if (r2 < tau * sq)
+              r2 = mma_exact_r2(a.cand + rows_i[i] * (long long)a.d, a.d, a.lb, a.range, tp + (jc + e) * ds);
+            mn[i] = fmin(mn[i], r2);
+            sum[i] = fma(rbf_phi_from_r2<KERN>(r2), e ? w2.y : w2.x, sum[i]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (tid == 0 && t + kMmaStages < ntiles) issue(t + kMmaStages);
+  }
+
+  // combine the quad's partial results (fixed order: deterministic)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], 1);
+    sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], 2);
+    mn[i] = fmin(mn[i], __shfl_xor_sync(0xffffffffu, mn[i], 1));
+    mn[i] = fmin(mn[i], __shfl_xor_sync(0xffffffffu, mn[i], 2));
+  }
+  // tail: lambda_0 + sum_k lambda_k u_k over this thread's dimensions, then across the quad
+  double fmn = inf, fmx = -inf, dmn = inf, dmx = -inf;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double ts = 0.0;
+    if (a.tail == B200RBF_TAIL_LINEAR) {
+#pragma unroll
+      for (int k = 0; k < K4; ++k) {
+        const int dim = 4 * k + tig;
+        if (dim < a.d) ts = fma(__ldg(a.tailc + 1 + dim), afr[i][k] + 0.5, ts);
+      }
+    }
+    ts += __shfl_xor_sync(0xffffffffu, ts, 1);
+    ts += __shfl_xor_sync(0xffffffffu, ts, 2);
+    const long long row = base + gid + 8 * i;
+    const bool live = row < a.m;
+    const double fval = sum[i] + (ts + __ldg(a.tailc));
+    double dval = 0.0;
+    if (a.min_mode != 0) dval = a.dscale * sqrt(mn[i]);
+    if (live && tig == 0) {
+      a.fvals[row] = fval;
+      if (a.min_mode != 0) {
+        if (a.min_mode == 2) dval = fmin(dval, a.dmerit[row]);
+        a.dmerit[row] = dval;
+      }
+    }
+    if (a.min_mode == 2) dval = __shfl_sync(0xffffffffu, dval, lane & ~3);  // the combined value lives in tig 0
+    if (live) {
+      fmn = fmin(fmn, fval);
+      fmx = fmax(fmx, fval);
+      dmn = fmin(dmn, dval);
+      dmx = fmax(dmx, dval);
+    }
+  }
+  fmn = warp_min(fmn);
+  fmx = warp_max(fmx);
+  dmn = warp_min(dmn);
+  dmx = warp_max(dmx);
+  constexpr int NW = kMmaThreads / 32;
+  if (lane == 0) {
+    s_red[warp] = fmn;
+    s_red[NW + warp] = fmx;
+    s_red[2 * NW + warp] = dmn;
+    s_red[3 * NW + warp] = dmx;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < NW; ++w) {
+      fmn = fmin(fmn, s_red[w]);
+      fmx = fmax(fmx, s_red[NW + w]);
+      dmn = fmin(dmn, s_red[2 * NW + w]);
+      dmx = fmax(dmx, s_red[3 * NW + w]);
+    }
+    const int slot = a.part_off + blockIdx.x;
+    a.parts[slot] = fmn;
+    a.parts[a.nparts + slot] = fmx;
+    if (a.min_mode != 0) {
+      a.parts[2 * a.nparts + slot] = dmn;
+      a.parts[3 * a.nparts + slot] = dmx;
+    }
+  }
+}
+
+inline size_t score_mma_smem_bytes(int ds) {
+  return ((size_t)kMmaStages * kMmaTileRows * ds + 2 * (size_t)kMmaStages * kMmaTileRows + kMmaStages +
+          4 * (kMmaThreads / 32)) * 8;
+}
+
+template <int K4, int KERN>
+int launch_score_mma_inst(b200rbf_ctx* h, const MmaArgs& ma) {
+  auto kern = score_mma_kernel<K4, KERN>;
+  const size_t smem = score_mma_smem_bytes(ma.ds);
+  B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (ma.s.occ_out != nullptr) {
+    B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(ma.s.occ_out, kern, kMmaThreads, smem));
+    return 0;
+  }
+  const long long blocks = (ma.s.m + kMmaThreads - 1) / kMmaThreads;
+  kern<<<(unsigned)blocks, kMmaThreads, smem, h->stream>>>(ma);
+  h->launches++;
+  B2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int K4>
+int launch_score_mma_k4(b200rbf_ctx* h, const MmaArgs& ma, int kernel) {
+  switch (kernel) {
+    case B200RBF_KERNEL_CUBIC: return launch_score_mma_inst<K4, B200RBF_KERNEL_CUBIC>(h, ma);
+    case B200RBF_KERNEL_TPS: return launch_score_mma_inst<K4, B200RBF_KERNEL_TPS>(h, ma);
+    default: return launch_score_mma_inst<K4, B200RBF_KERNEL_LINEAR>(h, ma);
+  }
+}
+
+// K4 = 1..16 (d <= 64), four per translation unit
+int launch_score_mma_group0(b200rbf_ctx*, const MmaArgs&, int k4, int kernel);
+int launch_score_mma_group1(b200rbf_ctx*, const MmaArgs&, int k4, int kernel);
+int launch_score_mma_group2(b200rbf_ctx*, const MmaArgs&, int k4, int kernel);
+int launch_score_mma_group3(b200rbf_ctx*, const MmaArgs&, int k4, int kernel);
+
+}  // namespace b200rbf

@@ -220,12 +220,17 @@ def check_selection(name, idx, g, orc, fv, dm):
             break  # later picks legitimately diverge after a tie
 
 
-@pytest.mark.parametrize("exact", [False, True])
-def test_merit_selection_golden(pb, orc, merit_cases, exact):
+@pytest.mark.parametrize("mode", ["mma", "direct", "exact"])
+def test_merit_selection_golden(pb, orc, merit_cases, mode):
+    """mma: norm expansion with DMMA dot products (default); direct: FMA differences; exact: cdist-identical."""
+    from pysot_b200 import _lib
+
+    exact = mode == "exact"
     for name in merit_cases.names:
         g = merit_cases.get(name)
         d = g["X"].shape[1]
         s = make_gpu(pb, d, g["lb"], g["ub"], str(g["kernel"]), str(g["tail"]), exact_dist=exact)
+        s.handle.set_option(_lib.OPT_MMA_DIST, 1 if mode == "mma" else 0)
         s.add_points(g["X"], g["fX"])
         p = len(g["weights"])
         idx, merit, fv, dm, st = pb.merit_select_indices(p, s, g["X"], g["cand"], list(g["weights"]), g.get("Xpend"),
@@ -236,7 +241,8 @@ def test_merit_selection_golden(pb, orc, merit_cases, exact):
         elif exact and np.any(g["ub"] - g["lb"] != (g["ub"] - g["lb"])[0]):
             assert np.array_equal(dm, g["dmerit0"].ravel()), name  # anisotropic box: original-space pass, exact
         else:
-            assert relmax(dm, g["dmerit0"].ravel()) < 1e-13, name
+            assert relmax(dm, g["dmerit0"].ravel()) < 1e-12, name
+            assert np.array_equal(dm == 0.0, g["dmerit0"].ravel() == 0.0), name  # coincident points stay exactly 0
         assert st[0] == fv.min() and st[1] == fv.max() and st[2] == dm.min() and st[3] == dm.max(), name
         check_selection(name, idx, g, orc, fv, dm)
         pts = pb.weighted_distance_merit(p, s, g["X"], g["fX"], g["cand"], list(g["weights"]), g.get("Xpend"),
@@ -309,7 +315,7 @@ def test_large_scoring_against_tiled_oracle(pb, orc):
     import torch
 
     rng = np.random.default_rng(4)
-    d, n, m = 50, 2000, 40000
+    d, n, m = 50, 2000, 120000  # > 2 waves of the score kernel (148 SMs x 3 CTAs x 128 rows): several chunks
     lb, ub = np.zeros(d), np.ones(d)
     X = rng.random((n, d))
     c = rng.standard_normal((n + d + 1, 1))
@@ -319,7 +325,7 @@ def test_large_scoring_against_tiled_oracle(pb, orc):
     s = pb.GpuRBFInterpolant(dim=d, lb=lb, ub=ub, exact_dist=True)
     s.add_points(X, np.zeros(n))
     s.set_coefficients(c)
-    s.handle.set_option(2, 8192)  # B200RBF_OPT_CHUNK_ROWS: 5 chunks
+    s.handle.set_option(2, 8192)  # B200RBF_OPT_CHUNK_ROWS: rounded up to one full wave per chunk -> 3 chunks
     o = orc.OracleRBF(d, lb, ub)
     o.add_points(X, np.zeros(n))
     o.c, o.updated = c, True
@@ -406,3 +412,35 @@ def test_dimensions_above_64_use_the_generic_kernel(pb, orc, d):
     big.add_points(rng.random((501, 500)), np.zeros(501))
     with pytest.raises(ValueError):  # beyond the generic kernel's shared-memory budget: refused, never a CPU fallback
         big.predict(np.zeros(500))
+
+
+def test_mma_and_direct_kernels_agree_on_clustered_points(pb, orc):
+    """Optimiser-like cloud: centers and candidates clustered around one point, many NEAR pairs (the DMMA kernel's
+    direct-recompute path), duplicates included; both kernels against the oracle."""
+    from pysot_b200 import _lib
+
+    rng = np.random.default_rng(11)
+    d, n, m = 30, 400, 6000
+    lb, ub = np.zeros(d), np.ones(d)
+    x0 = rng.random(d)
+    X = np.clip(x0 + 10.0 ** rng.uniform(-6, -0.5, (n, 1)) * rng.standard_normal((n, d)), 0, 1)
+    fX = ((X - x0) ** 2).sum(1, keepdims=True)
+    cand = np.clip(x0 + 10.0 ** rng.uniform(-7, -0.5, (m, 1)) * rng.standard_normal((m, d)), 0, 1)
+    cand[:50] = X[:50]
+    o = orc.OracleRBF(d, lb, ub)
+    o.add_points(X, fX)
+    tr = {}
+    orc.weighted_distance_merit(4, o, X, fX, cand.copy(), [0.3, 0.5, 0.8, 0.95], None, 1e-3, trace=tr)
+    res = {}
+    for mode in ("mma", "direct"):
+        s = pb.GpuRBFInterpolant(dim=d, lb=lb, ub=ub)
+        s.handle.set_option(_lib.OPT_MMA_DIST, 1 if mode == "mma" else 0)
+        s.add_points(X, fX)
+        s.set_coefficients(o.c)  # same coefficients: isolates the evaluation kernels from the (ill-conditioned) fit
+        idx, _, fv, dm, _ = pb.merit_select_indices(4, s, X, cand, [0.3, 0.5, 0.8, 0.95], None, want_scores=True)
+        res[mode] = (idx, fv, dm)
+        assert relmax(fv, tr["fvals_raw"].ravel()) < TOL, mode
+        assert np.all(dm[:50] == 0.0) and relmax(dm, tr["dmerit0"].ravel()) < 1e-12, mode
+        rel = np.abs(dm - tr["dmerit0"].ravel())[50:] / tr["dmerit0"].ravel()[50:]
+        assert rel.max() < 1e-9, (mode, rel.max())  # near pairs keep RELATIVE accuracy (direct recomputation)
+        assert np.array_equal(idx, tr["picked"]), mode

@@ -18,17 +18,20 @@ pytestmark = pytest.mark.gpu
 
 
 def test_config1_dycors_ackley10_serial():
-    ncalls, mismatches, ties, _, _ = replay("trace_dycors.npz", GpuBackend())
+    ncalls, mismatches, ties, _ = replay("trace_dycors.npz", GpuBackend())
     assert ncalls > 400 and not mismatches, (ncalls, ties, mismatches[:5])
 
 
 def test_config2_srbf_levy30_async8():
-    ncalls, mismatches, ties, _, _ = replay("trace_srbf.npz", GpuBackend())
+    ncalls, mismatches, ties, _ = replay("trace_srbf.npz", GpuBackend())
     assert ncalls > 1500 and not mismatches, (ncalls, ties, mismatches[:5])
 
 
 def test_config5_sop_rastrigin20_with_gradients():
-    ncalls, mismatches, ties, worst_pred, worst_deriv = replay("trace_sop.npz", GpuBackend())
+    ncalls, mismatches, ties, err = replay("trace_sop.npz", GpuBackend())
     assert ncalls > 400 and not mismatches, (ncalls, ties, mismatches[:5])
-    # the reference extends its LU incrementally, the GPU refits: the reference's own reorder noise
-    assert worst_pred < 1e-9 and worst_deriv < 1e-9, (worst_pred, worst_deriv)
+    # identical inputs through the reference's initial-fit branch (a fresh RBFInterpolant on the same points): 1e-10
+    assert err["pred_vs_fresh_fit"] < 1e-10 and err["deriv_vs_fresh_fit"] < 1e-10, err
+    # against the strategy's own incrementally-extended surrogate (rbf.py:132-161) the bar is the reference's own
+    # incremental-vs-fresh noise on this trace (2.1e-10 / 7.1e-9 pointwise, recorded in the fixture)
+    assert err["pred_vs_incremental"] < 1e-9 and err["deriv_vs_incremental"] < 1e-8, err

@@ -132,8 +132,10 @@ def test_strategy_trace_replay_with_the_oracle():
     oracle under teacher-forced replay -- this also pins the replay logic the GPU test relies on."""
     from trace_replay import OracleBackend, replay
 
-    ncalls, mismatches, ties, _, _ = replay("trace_dycors.npz", OracleBackend())
+    ncalls, mismatches, ties, _ = replay("trace_dycors.npz", OracleBackend())
     assert ncalls > 400 and not mismatches and ties == 0
     for fname in ("trace_srbf.npz", "trace_sop.npz"):
-        ncalls, mismatches, ties, wp, wd = replay(fname, OracleBackend(), max_calls=60)
-        assert ncalls == 60 and not mismatches and ties == 0 and wp < 1e-12 and wd < 1e-12
+        ncalls, mismatches, ties, err = replay(fname, OracleBackend(), max_calls=120)
+        assert ncalls == 120 and not mismatches and ties == 0
+        if err:  # the oracle extends its LU exactly like the reference: bit-identical to the recorded values
+            assert err["pred_vs_incremental"] == 0.0 and err["deriv_vs_incremental"] == 0.0

@@ -44,7 +44,7 @@ def replay(fname, backend, max_calls=None):
     seg, have = -1, 0
     pend_off = np.concatenate(([0], np.cumsum(g["pend_cnt"])))
     pt_off = np.concatenate(([0], np.cumsum(g["num_pts"])))
-    mismatches, ties, worst_deriv, worst_pred = [], 0, 0.0, 0.0
+    mismatches, ties, err = [], 0, {}
     for i in range(ncalls):
         if int(g["seg"][i]) != seg:  # restart: the strategy reset the surrogate (surrogate_strategy.py:228)
             s.reset()
@@ -77,7 +77,16 @@ def replay(fname, backend, max_calls=None):
                 ties += 1
             else:
                 mismatches.append((i, first, float(g["margins"][pt_off[i] + first])))
-        if "deriv" in g.files:  # config #5 add-on: gradient at every proposed point
-            worst_deriv = max(worst_deriv, relmax(s.predict_deriv(ref), g["deriv"][pt_off[i]:pt_off[i + 1]]))
-            worst_pred = max(worst_pred, relmax(s.predict(ref), g["pred"][pt_off[i]:pt_off[i + 1]]))
-    return ncalls, mismatches, ties, worst_pred, worst_deriv
+        if "deriv" in g.files:  # config #5 add-on: value and gradient at every proposed point
+            sl = slice(pt_off[i], pt_off[i + 1])
+            gd, gp = s.predict_deriv(ref), s.predict(ref)
+            for key in ("deriv", "deriv_full"):
+                err[key] = max(err.get(key, 0.0), float(np.max(np.abs(gd - g[key][sl]))))
+            for key in ("pred", "pred_full"):
+                err[key] = max(err.get(key, 0.0), float(np.max(np.abs(gp - g[key][sl]))))
+    if err:  # max |delta| / max |reference| over the whole trace (the north-star parity metric)
+        n_used = pt_off[ncalls]
+        sd, sp = float(np.max(np.abs(g["deriv_full"][:n_used]))), float(np.max(np.abs(g["pred_full"][:n_used])))
+        err = {"pred_vs_incremental": err["pred"] / sp, "deriv_vs_incremental": err["deriv"] / sd,
+               "pred_vs_fresh_fit": err["pred_full"] / sp, "deriv_vs_fresh_fit": err["deriv_full"] / sd}
+    return ncalls, mismatches, ties, err

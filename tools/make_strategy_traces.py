@@ -58,6 +58,10 @@ class Recorder:
         self.kind, self.ref_fn, self.want_deriv = kind, ref_fn, want_deriv
         self.calls, self.states, self.last_post = [], [], None
         self.strategy = None
+        # every row that ever was in the strategy's current-run arrays (_X, _fX), in order; a call refers to the
+        # contiguous slice [start, start + n).  (_X is NOT a slice of X: evaluations proposed before a radius
+        # change are added to X but not to _X, surrogate_strategy.py:426-428.)
+        self.runX, self.runfX, self.run_start, self.run_len = [], [], 0, 0
 
     def __call__(self, **kw):
         pre = np.random.get_state()
@@ -85,16 +89,28 @@ class Recorder:
         if not same_state(pre, self.last_post):
             self.states.append((len(self.calls), pre))
         self.last_post = post
-        st = self.strategy
-        rec = dict(n=kw["X"].shape[0], seg=len(st.X) - len(st._X), Xpend=np.array(kw.get("Xpend")),
+        Xc, fXc = kw["X"], kw["fX"]
+        n = Xc.shape[0]
+        cur = np.array(self.runX[self.run_start:self.run_start + min(n, self.run_len)]).reshape(-1, prob.dim)
+        if n < self.run_len or not np.array_equal(cur, Xc[:self.run_len]):  # restart: a new run begins
+            self.run_start, self.run_len = len(self.runX), 0
+        for r in range(self.run_len, n):
+            self.runX.append(Xc[r].copy())
+            self.runfX.append(fXc[r].copy())
+        self.run_len = n
+        rec = dict(n=n, seg=self.run_start, Xpend=np.array(kw.get("Xpend")),
                    weights=np.array(kw["weights"], dtype=float), num_pts=kw["num_pts"],
                    prob_perturb=kw.get("prob_perturb", np.nan), sampling_radius=kw.get("sampling_radius", 0.2),
                    num_cand=kw.get("num_cand") or 100 * prob.dim,
                    xbest=np.array(kw["xbest"]) if kw.get("xbest") is not None else np.full(prob.dim, np.nan),
                    new_points=pts.copy(), margins=np.array(margins), picked=tr["picked"].copy())
         if self.want_deriv:
-            rec["deriv"] = sur.predict_deriv(pts)
+            rec["deriv"] = sur.predict_deriv(pts)  # the strategy's surrogate: incrementally extended LU (rbf.py:132-161)
             rec["pred"] = sur.predict(pts)
+            fresh = RBFInterpolant(dim=prob.dim, lb=prob.lb, ub=prob.ub, kernel=CubicKernel(), tail=LinearTail(prob.dim))
+            fresh.add_points(sur.X, sur.fX)         # the same points through the reference's initial-fit branch
+            rec["deriv_full"] = fresh.predict_deriv(pts)
+            rec["pred_full"] = fresh.predict(pts)
         self.calls.append(rec)
         return pts
 
@@ -105,7 +121,7 @@ class Recorder:
         pend = [r["Xpend"].reshape(-1, d) for r in c]
         out = dict(
             kind=np.array(self.kind), dim=np.array(d), lb=prob.lb, ub=prob.ub, int_var=np.array(prob.int_var, dtype=np.int64),
-            allX=st.X, allfX=st.fX, n=np.array([r["n"] for r in c]), seg=np.array([r["seg"] for r in c]),
+            allX=np.array(self.runX), allfX=np.array(self.runfX).reshape(-1, 1), n=np.array([r["n"] for r in c]), seg=np.array([r["seg"] for r in c]),
             pend_cnt=np.array([p.shape[0] for p in pend]), pend=np.vstack(pend) if pend else np.empty((0, d)),
             num_pts=np.array([r["num_pts"] for r in c]), weights=np.concatenate([r["weights"] for r in c]),
             prob_perturb=np.array([r["prob_perturb"] for r in c]), sampling_radius=np.array([r["sampling_radius"] for r in c]),
@@ -116,8 +132,12 @@ class Recorder:
             state_pos=np.array([s[1][2] for s in self.states]), state_gauss=np.array([s[1][3] for s in self.states]),
             state_cached=np.array([s[1][4] for s in self.states]), **extra)
         if self.want_deriv:
-            out["deriv"] = np.vstack([r["deriv"] for r in c])
-            out["pred"] = np.vstack([r["pred"] for r in c])
+            for key in ("deriv", "pred", "deriv_full", "pred_full"):
+                out[key] = np.vstack([r[key] for r in c])
+            dn = max(np.max(np.abs(a["deriv"] - a["deriv_full"])) / np.max(np.abs(a["deriv_full"])) for a in c)
+            pn = max(np.max(np.abs(a["pred"] - a["pred_full"])) / np.max(np.abs(a["pred_full"])) for a in c)
+            print("reference incremental-vs-full noise: predict %.2e, predict_deriv %.2e (worst call)" % (pn, dn))
+            out["ref_noise_pred"], out["ref_noise_deriv"] = np.array(pn), np.array(dn)
         np.savez_compressed(os.path.join(OUT, fname), **out)
         size = os.path.getsize(os.path.join(OUT, fname)) / 1e6
         print("%s: %d calls, %d stored RNG states, %d evals, best %.4f, min margin %.2e, %.2f MB"
