@@ -62,7 +62,7 @@ __global__ void split_coef_kernel(const double* __restrict__ c, int t, int n, do
   if (i < npad) coef[i] = i < n ? c[t + i] : 0.0;
   if (i < t) tailc[i] = c[i];
 }
-// shifted (u - 0.5) centers with row stride ds and their squared norms (operands of score_mma_kernel)
+// centers with row stride ds and their squared norms (operands of score_mma_kernel)
 __global__ void mma_points_kernel(const double* __restrict__ src, int n, int d, double* __restrict__ dst, int npad,
                                   int ds, double* __restrict__ cnorm) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -70,7 +70,7 @@ __global__ void mma_points_kernel(const double* __restrict__ src, int n, int d, 
   const int si = i < n ? i : n - 1;
   double n2 = 0.0;
   for (int k = 0; k < ds; ++k) {
-    const double v = k < d ? src[(size_t)si * d + k] - 0.5 : 0.0;
+    const double v = k < d ? src[(size_t)si * d + k] : 0.0;
     dst[(size_t)i * ds + k] = v;
     n2 = fma(v, v, n2);
   }

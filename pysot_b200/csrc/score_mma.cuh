@@ -6,12 +6,11 @@
 // of d subtractions + d FMAs (1.65x fewer FP64-pipe cycles at d = 50), with 15x fewer shared-memory loads because
 // the MMA reuses each center element across 32 candidates.
 //
-// Accuracy.  Coordinates are shifted by 0.5 (centre of the unit box) so |u|^2 + |c|^2 ~ d/6 instead of 2d/3.  The
-// expansion's absolute error in r^2 is ~ eps (|u|^2 + |c|^2); where that is not negligible relative to r^2 itself,
-// i.e. for NEAR pairs with r^2 < 2^-10 (|u|^2 + |c|^2), the pair is recomputed with direct differences (rare,
-// divergent slow path), so coincident points still give r = 0 exactly and `dmerit < dtol` (candidate_srbf.py:48)
-// is decided on a distance with full relative accuracy.  Elsewhere the relative error of r^2 is <= ~1e-12, far
-// inside the 1e-10 parity bar; `exact_dist` mode never uses this kernel.
+// Accuracy.  The expansion's absolute error in r^2 is ~ eps (|u|^2 + |c|^2); where that is not negligible relative to
+// r^2 itself, i.e. for NEAR pairs with r^2 < 2^-10 (|u|^2 + |c|^2), the pair is recomputed with direct differences in
+// exactly the arithmetic of score_kernel (rare, divergent slow path), so coincident points still give r = 0 exactly
+// and `dmerit < dtol` (candidate_srbf.py:48) is decided on a distance with full relative accuracy.  Elsewhere the
+// relative error of r^2 is <= ~1e-12, far inside the 1e-10 parity bar; `exact_dist` mode never uses this kernel.
 //
 // Work decomposition: one warp owns 32 candidates (4 m8 blocks).  Thread (gid = lane / 4, tig = lane % 4) holds
 // the A fragments u[gid + 8 i][4 k + tig] in registers for the whole kernel and receives, per 8-center block, the
@@ -46,7 +45,7 @@ static __device__ __noinline__ double mma_exact_r2(const double* __restrict__ sr
   for (int k = 0; k < d; ++k) {
     double v = __ldg(src + k);
     if (lb != nullptr) v = __ddiv_rn(__dsub_rn(v, __ldg(lb + k)), __ldg(range + k));
-    const double t = (v - 0.5) - cp[k];
+    const double t = v - cp[k];  // same arithmetic as score_kernel: near pairs are bit-identical to the direct path
     acc = fma(t, t, acc);
   }
   return acc;
@@ -102,7 +101,6 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(MmaArgs ma) {
       if (dim < a.d) {
         v = __ldg(src + dim);
         if (a.lb != nullptr) v = __ddiv_rn(__dsub_rn(v, __ldg(a.lb + dim)), __ldg(a.range + dim));
-        v -= 0.5;
       }
       afr[i][k] = v;
       n2 = fma(v, v, n2);
@@ -181,7 +179,7 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(MmaArgs ma) {
 #pragma unroll
       for (int k = 0; k < K4; ++k) {
         const int dim = 4 * k + tig;
-        if (dim < a.d) ts = fma(__ldg(a.tailc + 1 + dim), afr[i][k] + 0.5, ts);
+        if (dim < a.d) ts = fma(__ldg(a.tailc + 1 + dim), afr[i][k], ts);
       }
     }
     ts += __shfl_xor_sync(0xffffffffu, ts, 1);
