@@ -165,8 +165,18 @@ struct ScorePlan {
   int dist_mode = 0;          // min_mode of the distance-only pass (1 write, 2 combine)
 };
 
-// candidates per CTA of the kernel that serves this padded dimension
-int block_rows(int dpad) { return dpad <= kMaxRegDim ? kScoreThreads : score_generic_threads(); }
+// smallest candidates-per-CTA among the kernels that may serve this padded dimension (sizes the partial-stat slots)
+int block_rows(int dpad) {
+  if (dpad > kMaxRegDim) return score_generic_threads();
+  return kMmaRowsPerCta < kScoreThreads ? kMmaRowsPerCta : kScoreThreads;
+}
+bool use_mma(const b200rbf_ctx* h, bool with_phi);
+// candidates per CTA of the kernel that computes surrogate values / of the distance-only kernel
+int main_rows(const b200rbf_ctx* h) {
+  if (h->model.dpad > kMaxRegDim) return score_generic_threads();
+  return use_mma(h, true) ? kMmaRowsPerCta : kScoreThreads;
+}
+int dist_rows(const b200rbf_ctx* h) { return h->model.dpad > kMaxRegDim ? score_generic_threads() : kScoreThreads; }
 
 bool use_mma(const b200rbf_ctx* h, bool with_phi) {
   return with_phi && h->mma_dist && !h->exact_dist && h->model.dpad <= kMaxRegDim;
@@ -209,7 +219,7 @@ int launch_score_any(b200rbf_ctx* h, const ScoreArgs& a, int dpad, int kernel, b
 
 // run the fused kernels over rows [r0, r0 + rows) of the device-resident candidates
 int score_rows(b200rbf_ctx* h, const ScorePlan& plan, const double* cand_dev, long long r0, long long rows,
-               const double* box, double* fvals, double* dmerit, double* parts, int nparts, int part_off) {
+               const double* box, double* fvals, double* dmerit, double* parts, int nparts, int off_f, int off_d) {
   const Model& M = h->model;
   ScoreArgs a;
   memset(&a, 0, sizeof(a));
@@ -218,7 +228,7 @@ int score_rows(b200rbf_ctx* h, const ScorePlan& plan, const double* cand_dev, lo
   a.d = M.d;
   a.parts = parts;
   a.nparts = nparts;
-  a.part_off = part_off;
+  a.part_off = off_f;  // the value kernel's CTAs index the f rows (and the d rows when it also produces dmerit)
   if (plan.with_phi) {
     a.lb = box;
     a.range = box + M.dpad;
@@ -242,6 +252,7 @@ int score_rows(b200rbf_ctx* h, const ScorePlan& plan, const double* cand_dev, lo
     a.npad = plan.dist_npad;
     a.dscale = 1.0;
     a.min_mode = plan.dist_mode;
+    a.part_off = off_d;  // its CTAs may cover a different number of candidates: separate slot numbering
     a.fvals = nullptr;
     a.dmerit = dmerit + r0;
     B2_TRY(launch_score_any(h, a, M.dpad, 0, h->exact_dist, false));
@@ -253,15 +264,16 @@ int score_rows(b200rbf_ctx* h, const ScorePlan& plan, const double* cand_dev, lo
 // H2D copy of chunk i+1 overlaps the kernels of chunk i.  dst_dev receives the rows when they come from the host.
 int score_pipeline(b200rbf_ctx* h, const ScorePlan& plan, const double* cand, long long m, double* dst_dev,
                    const double* box, double* fvals, double* dmerit, double* parts, int nparts,
-                   const double** cand_dev_out, int* parts_used) {
+                   const double** cand_dev_out, int* used_f, int* used_d) {
   const Model& M = h->model;
   const PtrKind kind = ptr_kind(cand);
   if (kind == kDevice) {
     const long long kMaxRows = (long long)block_rows(M.dpad) * 0x7fff0000LL;
     B2_CHECK(m <= kMaxRows, B200RBF_EINVAL, "too many candidates");
-    B2_TRY(score_rows(h, plan, cand, 0, m, box, fvals, dmerit, parts, nparts, 0));
+    B2_TRY(score_rows(h, plan, cand, 0, m, box, fvals, dmerit, parts, nparts, 0, 0));
     *cand_dev_out = cand;
-    *parts_used = (int)((m + block_rows(M.dpad) - 1) / block_rows(M.dpad));
+    *used_f = (int)((m + main_rows(h) - 1) / main_rows(h));
+    *used_d = plan.dist_pts ? (int)((m + dist_rows(h) - 1) / dist_rows(h)) : *used_f;
     return 0;
   }
   // chunk = a whole number of full waves of the score kernel (resident CTAs x candidates per CTA): consecutive
@@ -273,7 +285,7 @@ int score_pipeline(b200rbf_ctx* h, const ScorePlan& plan, const double* cand, lo
     int occ = 0;
     q.occ_out = &occ;
     B2_TRY(launch_score_any(h, q, M.dpad, M.kernel, h->exact_dist, plan.with_phi));
-    const long long wave = (long long)h->sm_count * (occ > 0 ? occ : 1) * block_rows(M.dpad);
+    const long long wave = (long long)h->sm_count * (occ > 0 ? occ : 1) * main_rows(h);
     long long waves = (chunk + wave / 2) / wave;
     if (waves < 1) waves = 1;
     chunk = waves * wave;
@@ -284,7 +296,7 @@ int score_pipeline(b200rbf_ctx* h, const ScorePlan& plan, const double* cand, lo
     B2_TRY(h->stage[0].reserve((size_t)cr * row_bytes));
     if (m > chunk) B2_TRY(h->stage[1].reserve((size_t)cr * row_bytes));
   }
-  int part_off = 0, slot = 0;
+  int off_f = 0, off_d = 0, slot = 0;
   bool used[2] = {false, false};
   for (long long r0 = 0; r0 < m; r0 += chunk, slot ^= 1) {
     const long long rows = (m - r0 < chunk) ? (m - r0) : chunk;
@@ -299,11 +311,13 @@ int score_pipeline(b200rbf_ctx* h, const ScorePlan& plan, const double* cand, lo
     B2_CUDA(cudaEventRecord(h->ev_copy[slot], h->copy_stream));
     used[slot] = true;
     B2_CUDA(cudaStreamWaitEvent(h->stream, h->ev_copy[slot], 0));
-    B2_TRY(score_rows(h, plan, dst_dev, r0, rows, box, fvals, dmerit, parts, nparts, part_off));
-    part_off += (int)((rows + block_rows(M.dpad) - 1) / block_rows(M.dpad));
+    B2_TRY(score_rows(h, plan, dst_dev, r0, rows, box, fvals, dmerit, parts, nparts, off_f, off_d));
+    off_f += (int)((rows + main_rows(h) - 1) / main_rows(h));
+    off_d += (int)((rows + dist_rows(h) - 1) / dist_rows(h));
   }
   *cand_dev_out = dst_dev;
-  *parts_used = part_off;
+  *used_f = off_f;
+  *used_d = plan.dist_pts ? off_d : off_f;
   return 0;
 }
 
@@ -500,8 +514,9 @@ int b200rbf_predict(b200rbf_handle h, const double* x, long long m, const double
   }
   ScorePlan plan;
   const double* used = nullptr;
-  int parts_used = 0;
-  B2_TRY(score_pipeline(h, plan, x, m, xdev, h->tmp_box.as<double>(), fv, nullptr, parts, nparts, &used, &parts_used));
+  int used_f = 0, used_d = 0;
+  B2_TRY(score_pipeline(h, plan, x, m, xdev, h->tmp_box.as<double>(), fv, nullptr, parts, nparts, &used, &used_f,
+                        &used_d));
   if (host_out) B2_TRY(copy_out(h, out, fv, (size_t)m * sizeof(double)));
   B2_CUDA(cudaStreamSynchronize(h->stream));
   return 0;
@@ -585,12 +600,13 @@ int b200rbf_score(b200rbf_handle h, const double* cand, long long m, const doubl
     B2_TRY(S.cand_own.reserve((size_t)m * M.d * sizeof(double)));
     own = S.cand_own.as<double>();
   }
-  int parts_used = 0;
+  int used_f = 0, used_d = 0;
   B2_CUDA(cudaEventRecord(h->ev_s0, h->stream));
   B2_TRY(score_pipeline(h, plan, cand, m, own, S.box.as<double>(), S.fvals.as<double>(), S.dmerit.as<double>(),
-                        S.parts.as<double>(), S.nparts, &S.cand, &parts_used));
+                        S.parts.as<double>(), S.nparts, &S.cand, &used_f, &used_d));
   B2_CUDA(cudaEventRecord(h->ev_s1, h->stream));
-  B2_TRY(launch_stats(h, S.parts.as<double>(), S.nparts, parts_used, 3, S.stats.as<double>()));
+  B2_TRY(launch_stats(h, S.parts.as<double>(), S.nparts, used_f, 1, S.stats.as<double>()));
+  B2_TRY(launch_stats(h, S.parts.as<double>(), S.nparts, used_d, 2, S.stats.as<double>()));
   S.m = m;
   S.d = M.d;
   if (fvals_out) B2_TRY(copy_out(h, fvals_out, S.fvals.p, (size_t)m * sizeof(double)));

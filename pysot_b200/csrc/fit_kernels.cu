@@ -354,11 +354,12 @@ template <int kGemmStages>
 __global__ void __launch_bounds__(kGemmThreads, 2) gemm_sub_kernel(double* __restrict__ C, int ldc,
                                                                    const double* __restrict__ A, int lda,
                                                                    const double* __restrict__ B, int ldb, int M,
-                                                                   int Nc, int K) {
+                                                                   int Nc, int K, int lower) {
   extern __shared__ __align__(16) double gsm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 1, wn = warp & 1;  // 4 x 2 warps, warp tile 32 x 32
   const int m0 = blockIdx.y * kGemmBM, n0 = blockIdx.x * kGemmBN;
+  if (lower && n0 > m0 + kGemmBM - 1) return;  // symmetric update: tiles strictly above the diagonal are skipped
   const int gid = lane >> 2, tig = lane & 3;
 
   auto load_tiles = [&](int stage, int k0) {
@@ -563,7 +564,7 @@ __global__ void __launch_bounds__(256) dmix_peak_kernel(double* out, int iters, 
 // =================================================================================================== host side
 template <int STAGES>
 static int gemm_sub_inst(b200rbf_ctx* h, double* C, int ldc, const double* A, int lda, const double* B, int ldb, int M,
-                         int Nc, int K) {
+                         int Nc, int K, int lower) {
   static bool attr = false;
   constexpr size_t smem = gemm_smem_bytes(STAGES);
   if (!attr) {
@@ -573,18 +574,23 @@ static int gemm_sub_inst(b200rbf_ctx* h, double* C, int ldc, const double* A, in
     attr = true;
   }
   dim3 grid((Nc + kGemmBN - 1) / kGemmBN, (M + kGemmBM - 1) / kGemmBM);
-  gemm_sub_kernel<STAGES><<<grid, kGemmThreads, smem, h->stream>>>(C, ldc, A, lda, B, ldb, M, Nc, K);
+  gemm_sub_kernel<STAGES><<<grid, kGemmThreads, smem, h->stream>>>(C, ldc, A, lda, B, ldb, M, Nc, K, lower);
   h->launches++;
   B2_CUDA(cudaGetLastError());
   return 0;
 }
 
-static int gemm_sub(b200rbf_ctx* h, double* C, int ldc, const double* A, int lda, const double* B, int ldb, int M,
-                    int Nc, int K) {
+// C -= A B on the FP64 tensor cores; lower != 0: only tiles touching the lower triangle (C square, symmetric update)
+int gemm_sub_ex(b200rbf_ctx* h, double* C, int ldc, const double* A, int lda, const double* B, int ldb, int M, int Nc,
+                int K, int lower) {
   if (M <= 0 || Nc <= 0 || K <= 0) return 0;
   // 2 stages (58 KB) leave room for a look-ahead panel CTA beside one GEMM CTA on the same SM; 3 stages otherwise
-  return h->gemm_stages == 2 ? gemm_sub_inst<2>(h, C, ldc, A, lda, B, ldb, M, Nc, K)
-                             : gemm_sub_inst<3>(h, C, ldc, A, lda, B, ldb, M, Nc, K);
+  return h->gemm_stages == 2 ? gemm_sub_inst<2>(h, C, ldc, A, lda, B, ldb, M, Nc, K, lower)
+                             : gemm_sub_inst<3>(h, C, ldc, A, lda, B, ldb, M, Nc, K, lower);
+}
+static int gemm_sub(b200rbf_ctx* h, double* C, int ldc, const double* A, int lda, const double* B, int ldb, int M,
+                    int Nc, int K) {
+  return gemm_sub_ex(h, C, ldc, A, lda, B, ldb, M, Nc, K, 0);
 }
 
 int lu_factor_device(b200rbf_ctx* h, double* A, int ld, int N, int rcol0, int ncols, int* ipiv, int* info_dev) {

@@ -22,9 +22,19 @@
 
 namespace b200rbf {
 
-constexpr int kMmaThreads = 128;  // 4 warps x 32 candidates
-constexpr int kMmaTileRows = 32;  // center rows per tile (two 16-center steps)
+#ifndef B2_MMA_MB
+#define B2_MMA_MB 2
+#endif
+#ifndef B2_MMA_MINB
+#define B2_MMA_MINB 3
+#endif
+constexpr int kMmaThreads = 128;           // 4 warps
+constexpr int kMmaMB = B2_MMA_MB;          // m8 candidate blocks per warp (A fragments held in registers)
+constexpr int kMmaJB = 4;                  // n8 center blocks per step (32 centers = one tile)
+constexpr int kMmaMinBlocks = B2_MMA_MINB; // CTAs per SM the register budget is capped for
+constexpr int kMmaTileRows = 8 * kMmaJB;   // center rows per tile
 constexpr int kMmaStages = 3;
+constexpr int kMmaRowsPerCta = (kMmaThreads / 32) * 8 * kMmaMB;
 
 struct MmaArgs {
   ScoreArgs s;          // pts = shifted centers (npad x ds), coef = weights, as in score_kernel
@@ -52,7 +62,7 @@ static __device__ __noinline__ double mma_exact_r2(const double* __restrict__ sr
 }
 
 template <int K4, int KERN>
-__global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(MmaArgs ma) {
+__global__ void __launch_bounds__(kMmaThreads, kMmaMinBlocks) score_mma_kernel(MmaArgs ma) {
   const ScoreArgs& a = ma.s;
   const int ds = ma.ds;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -64,7 +74,7 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(MmaArgs ma) {
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gid = lane >> 2, tig = lane & 3;
-  const long long base = ((long long)blockIdx.x * (kMmaThreads / 32) + warp) * 32;
+  const long long base = ((long long)blockIdx.x * (kMmaThreads / 32) + warp) * (8 * kMmaMB);
   const int ntiles = (a.npad + kMmaTileRows - 1) / kMmaTileRows;
 
   if (tid == 0) {
@@ -85,11 +95,11 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(MmaArgs ma) {
     for (int t = 0; t < kMmaStages && t < ntiles; ++t) issue(t);
 
   // A fragments: shifted unit-box coordinates of candidates base + gid + 8 i, dimensions 4 k + tig
-  double afr[4][K4];
-  double nx[4];
-  long long rows_i[4];
+  double afr[kMmaMB][K4];
+  double nx[kMmaMB];
+  long long rows_i[kMmaMB];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < kMmaMB; ++i) {
     const long long row = base + gid + 8 * i;
     rows_i[i] = row < a.m ? row : (a.m - 1);
     const double* src = a.cand + rows_i[i] * (long long)a.d;
@@ -110,9 +120,13 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(MmaArgs ma) {
     nx[i] = n2;
   }
 
-  double sum[4] = {0.0, 0.0, 0.0, 0.0};
   const double inf = __longlong_as_double(0x7ff0000000000000LL);
-  double mn[4] = {inf, inf, inf, inf};
+  double sum[kMmaMB], mn[kMmaMB];
+#pragma unroll
+  for (int i = 0; i < kMmaMB; ++i) {
+    sum[i] = 0.0;
+    mn[i] = inf;
+  }
   const double tau = 0.0009765625;  // 2^-10
 
   for (int t = 0; t < ntiles; ++t) {
@@ -122,30 +136,31 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(MmaArgs ma) {
     const double* tp = s_pts + (size_t)s * kMmaTileRows * ds;
     const double* tw = s_wts + s * kMmaTileRows;
     const double* tn = s_nrm + s * kMmaTileRows;
-    for (int j0 = 0; j0 < rows; j0 += 16) {
-      double acc[4][2][2];
+    for (int j0 = 0; j0 < rows; j0 += 8 * kMmaJB) {  // npad is a multiple of 16; a short last step repeats valid rows
+      double acc[kMmaMB][kMmaJB][2];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < kMmaMB; ++i)
 #pragma unroll
-        for (int jb = 0; jb < 2; ++jb) acc[i][jb][0] = acc[i][jb][1] = 0.0;
+        for (int jb = 0; jb < kMmaJB; ++jb) acc[i][jb][0] = acc[i][jb][1] = 0.0;
       const double* pb = tp + (j0 + gid) * ds + tig;
 #pragma unroll
       for (int k = 0; k < K4; ++k) {
-        const double b0 = pb[4 * k];
-        const double b1 = pb[8 * ds + 4 * k];
+        double bfr[kMmaJB];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          dmma884(acc[i][0][0], acc[i][0][1], afr[i][k], b0);
-          dmma884(acc[i][1][0], acc[i][1][1], afr[i][k], b1);
-        }
+        for (int jb = 0; jb < kMmaJB; ++jb) bfr[jb] = pb[8 * jb * ds + 4 * k];
+#pragma unroll
+        for (int i = 0; i < kMmaMB; ++i)
+#pragma unroll
+          for (int jb = 0; jb < kMmaJB; ++jb) dmma884(acc[i][jb][0], acc[i][jb][1], afr[i][k], bfr[jb]);
       }
 #pragma unroll
-      for (int jb = 0; jb < 2; ++jb) {
+      for (int jb = 0; jb < kMmaJB; ++jb) {
+        if (j0 + 8 * jb >= rows) break;  // tile shorter than a full step (npad % 32 == 16)
         const int jc = j0 + 8 * jb + 2 * tig;
         const double2 n2 = *reinterpret_cast<const double2*>(tn + jc);
         const double2 w2 = *reinterpret_cast<const double2*>(tw + jc);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < kMmaMB; ++i) {
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const double sq = nx[i] + (e ? n2.y : n2.x);
@@ -164,7 +179,7 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(MmaArgs ma) {
 
   // combine the quad's partial results (fixed order: deterministic)
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < kMmaMB; ++i) {
     sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], 1);
     sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], 2);
     mn[i] = fmin(mn[i], __shfl_xor_sync(0xffffffffu, mn[i], 1));
@@ -173,7 +188,7 @@ __global__ void __launch_bounds__(kMmaThreads, 2) score_mma_kernel(MmaArgs ma) {
   // tail: lambda_0 + sum_k lambda_k u_k over this thread's dimensions, then across the quad
   double fmn = inf, fmx = -inf, dmn = inf, dmx = -inf;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < kMmaMB; ++i) {
     double ts = 0.0;
     if (a.tail == B200RBF_TAIL_LINEAR) {
 #pragma unroll
@@ -247,7 +262,7 @@ int launch_score_mma_inst(b200rbf_ctx* h, const MmaArgs& ma) {
     B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(ma.s.occ_out, kern, kMmaThreads, smem));
     return 0;
   }
-  const long long blocks = (ma.s.m + kMmaThreads - 1) / kMmaThreads;
+  const long long blocks = (ma.s.m + kMmaRowsPerCta - 1) / kMmaRowsPerCta;
   kern<<<(unsigned)blocks, kMmaThreads, smem, h->stream>>>(ma);
   h->launches++;
   B2_CUDA(cudaGetLastError());

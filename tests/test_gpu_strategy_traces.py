@@ -30,8 +30,14 @@ def test_config2_srbf_levy30_async8():
 def test_config5_sop_rastrigin20_with_gradients():
     ncalls, mismatches, ties, err = replay("trace_sop.npz", GpuBackend())
     assert ncalls > 400 and not mismatches, (ncalls, ties, mismatches[:5])
-    # identical inputs through the reference's initial-fit branch (a fresh RBFInterpolant on the same points): 1e-10
-    assert err["pred_vs_fresh_fit"] < 1e-10 and err["deriv_vs_fresh_fit"] < 1e-10, err
+    # identical inputs through the reference's initial-fit branch (a fresh RBFInterpolant on the same points):
+    # predictions within 1e-10.  Gradients on this optimiser-like clustered cloud are bounded by the reference's OWN
+    # fresh-vs-incremental disagreement on the same trace (7.1e-9, stored in the fixture): two partial-pivoting LUs with
+    # different elimination orders cannot agree better than that here (hard part 2).
+    import numpy as np
+    from conftest import GOLDEN
+    noise = float(np.load(GOLDEN + "/trace_sop.npz")["ref_noise_deriv"])
+    assert err["pred_vs_fresh_fit"] < 1e-10 and err["deriv_vs_fresh_fit"] < max(1e-10, noise), (err, noise)
     # against the strategy's own incrementally-extended surrogate (rbf.py:132-161) the bar is the reference's own
     # incremental-vs-fresh noise on this trace (2.1e-10 / 7.1e-9 pointwise, recorded in the fixture)
     assert err["pred_vs_incremental"] < 1e-9 and err["deriv_vs_incremental"] < 1e-8, err
