@@ -26,12 +26,13 @@ namespace b200rbf {
 #define B2_MMA_MB 2
 #endif
 #ifndef B2_MMA_MINB
-#define B2_MMA_MINB 3
+#define B2_MMA_MINB 4
 #endif
 constexpr int kMmaThreads = 128;           // 4 warps
 constexpr int kMmaMB = B2_MMA_MB;          // m8 candidate blocks per warp (A fragments held in registers)
 constexpr int kMmaJB = 4;                  // n8 center blocks per step (32 centers = one tile)
-constexpr int kMmaMinBlocks = B2_MMA_MINB; // CTAs per SM the register budget is capped for
+constexpr int kMmaMinBlocks = B2_MMA_MINB; // CTAs per SM the register budget is capped for (+1 when d <= 16);
+                                           // tools/k2x_tune.cu sweep: 2 x 4 beats 2 x 3 by 6 %, 4 x 2 by 16 % at d = 50
 constexpr int kMmaTileRows = 8 * kMmaJB;   // center rows per tile
 constexpr int kMmaStages = 3;
 constexpr int kMmaRowsPerCta = (kMmaThreads / 32) * 8 * kMmaMB;
@@ -62,7 +63,7 @@ static __device__ __noinline__ double mma_exact_r2(const double* __restrict__ sr
 }
 
 template <int K4, int KERN>
-__global__ void __launch_bounds__(kMmaThreads, kMmaMinBlocks) score_mma_kernel(MmaArgs ma) {
+__global__ void __launch_bounds__(kMmaThreads, (K4 <= 4 ? kMmaMinBlocks + 1 : kMmaMinBlocks)) score_mma_kernel(MmaArgs ma) {
   const ScoreArgs& a = ma.s;
   const int ds = ma.ds;
   extern __shared__ __align__(128) unsigned char smem_raw[];
