@@ -56,7 +56,10 @@ enum {
   /* 1 (default): surrogate values use the norm expansion |u|^2 + |c|^2 - 2 u.c with the dot products on the FP64
    *    tensor path and a direct recomputation of near pairs (score_mma.cuh; ~1.6x fewer FP64 cycles at d = 50,
    *    relative error of r^2 <= ~1e-12).  0: direct differences everywhere.  Ignored when EXACT_DIST is set.     */
-  B200RBF_OPT_MMA_DIST = 6
+  B200RBF_OPT_MMA_DIST = 6,
+  /* solver of b200rbf_fit: 0 (default) auto = null-space Cholesky for cubic / TPS + linear tail with n >= 768, pivoted
+   *    LU otherwise and whenever the Cholesky reports a non-positive pivot; 1 = always LU; 2 = Cholesky or error       */
+  B200RBF_OPT_FIT_METHOD = 7
 };
 
 const char* b200rbf_last_error(void);
@@ -73,7 +76,9 @@ int b200rbf_set_stream(b200rbf_handle h, void* cuda_stream, int use_own);
 int b200rbf_set_option(b200rbf_handle h, int option, long long value);
 
 /* RBFInterpolant._fit, initial branch + coefficient solve (rbf.py:110-130, 164-168):
- *   A = [[0, P^T], [P, phi(cdist(Xu, Xu)) + eta I]],  c = A^-1 [0; rhs]   by LU with partial pivoting.
+ *   A = [[0, P^T], [P, phi(cdist(Xu, Xu)) + eta I]],  c = A^-1 [0; rhs]
+ * by LU with partial pivoting, or -- same solution, half the flops, no pivoting -- by a Cholesky factorisation of
+ * the system projected on null(P^T) when the kernel is conditionally positive definite (B200RBF_OPT_FIT_METHOD).
  * Xu: n x d centers already mapped to the unit box (surrogate.py:71); rhs: n transformed values
  * (output_transformation(fX), rbf.py:164).  c_out: n + ntail coefficients, tail first (rbf.py:183-184),
  * ntail = d + 1 (linear tail) or 1 (constant).  Centers and coefficients stay resident for predict /
@@ -140,6 +145,8 @@ long long b200rbf_launch_count(b200rbf_handle h);
 /* Device time (ms, CUDA events on the handle's stream) of the fused score kernel(s) of the last b200rbf_score;
  * with host candidates it spans the chunk pipeline including the waits on the H2D copies. */
 double b200rbf_last_score_ms(b200rbf_handle h);
+/* Solver the last b200rbf_fit used: 1 = pivoted LU, 2 = null-space Cholesky. */
+int b200rbf_last_fit_method(b200rbf_handle h);
 
 /* ---- test hooks: exercise the factorisation pieces in isolation (tests/ only, not the drop-in surface) ----
  * dbg_lu  : A_host is N x (N + nrhs) row-major; on return the leading N x N block holds L\U (unit lower L),

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libb200rbf.so")
 
 KERNEL_CUBIC, KERNEL_TPS, KERNEL_LINEAR = 0, 1, 2
 TAIL_LINEAR, TAIL_CONSTANT = 0, 1
-OPT_EXACT_DIST, OPT_CHUNK_ROWS, OPT_LU_PANEL, OPT_LU_LOOKAHEAD, OPT_GEMM_STAGES, OPT_MMA_DIST = 1, 2, 3, 4, 5, 6
+OPT_EXACT_DIST, OPT_CHUNK_ROWS, OPT_LU_PANEL, OPT_LU_LOOKAHEAD, OPT_GEMM_STAGES, OPT_MMA_DIST, OPT_FIT_METHOD = 1, 2, 3, 4, 5, 6, 7
 E_INVAL, E_CUDA, E_STATE, E_SINGULAR, E_NOMEM = -1, -2, -3, -4, -5
 
 _dp = C.POINTER(C.c_double)
@@ -39,6 +39,7 @@ PROTOTYPES = {
     "b200rbf_fp64_peaks": (C.c_int, [_vp, C.c_double, _vp]),
     "b200rbf_launch_count": (C.c_longlong, [_vp]),
     "b200rbf_last_score_ms": (C.c_double, [_vp]),
+    "b200rbf_last_fit_method": (C.c_int, [_vp]),
     "b200rbf_dbg_lu": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp]),
     "b200rbf_dbg_gemm": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _dp]),
 }
@@ -134,6 +135,10 @@ class Handle:
     @property
     def last_score_ms(self):
         return float(load().b200rbf_last_score_ms(self._h))
+
+    @property
+    def last_fit_method(self):
+        return {1: "lu", 2: "cholesky"}.get(int(load().b200rbf_last_fit_method(self._h)), "none")
 
     # ---- model
     def fit(self, Xu, rhs, kernel, tail, eta):

@@ -14,6 +14,10 @@ void set_error(const char* fmt, ...) {
 }
 
 int deriv_scratch_doubles(const b200rbf_ctx* h, long long m, size_t* out);
+int chol_fit_weights(b200rbf_ctx* h, const double* Xu_dev, const double* f_dev, int n, int d, int kernel, double eta,
+                     CholWork* wk, int* info_dev);
+int chol_fit_tail(b200rbf_ctx* h, const CholWork& w, const double* f_dev, const double* g_dev, double eta,
+                  double* c_full_dev);
 int run_lu_debug(b200rbf_ctx* h, double* A_dev, int ld, int N, int rcol0, int ncols, int* ipiv_dev, int* info_dev);
 int run_gemm_debug(b200rbf_ctx* h, double* C, int ldc, const double* A, int lda, const double* B, int ldb, int M,
                    int Nc, int K);
@@ -391,7 +395,7 @@ int b200rbf_destroy(b200rbf_handle h) {
   S.cand_own.release(); S.fvals.release(); S.dmerit.release(); S.parts.release(); S.pair_parts.release();
   S.stats.release(); S.winner.release(); S.results.release(); S.dist.release(); S.box.release();
   FitState& F = h->fit;
-  F.A.release(); F.piv.release(); F.rhs.release(); F.work.release(); F.flags.release();
+  F.A.release(); F.piv.release(); F.rhs.release(); F.work.release(); F.flags.release(); F.chol.release();
   h->tmp_in.release(); h->tmp_out.release(); h->tmp_box.release();
   h->stage[0].release(); h->stage[1].release(); h->pin_small.release();
   for (int i = 0; i < 2; ++i) cudaEventDestroy(h->ev_copy[i]);
@@ -417,6 +421,10 @@ int b200rbf_set_option(b200rbf_handle h, int option, long long value) {
   switch (option) {
     case B200RBF_OPT_EXACT_DIST: h->exact_dist = value != 0; return 0;
     case B200RBF_OPT_MMA_DIST: h->mma_dist = value != 0; return 0;
+    case B200RBF_OPT_FIT_METHOD:
+      B2_CHECK(value >= 0 && value <= 2, B200RBF_EINVAL, "fit method must be 0 (auto), 1 (LU) or 2 (Cholesky)");
+      h->fit_method = (int)value;
+      return 0;
     case B200RBF_OPT_CHUNK_ROWS:
       B2_CHECK(value >= 256, B200RBF_EINVAL, "chunk rows must be >= 256");
       h->chunk_rows = value;
@@ -438,6 +446,7 @@ int b200rbf_set_option(b200rbf_handle h, int option, long long value) {
 
 long long b200rbf_launch_count(b200rbf_handle h) { return h ? h->launches : 0; }
 double b200rbf_last_score_ms(b200rbf_handle h) { return h ? h->last_score_ms : -1.0; }
+int b200rbf_last_fit_method(b200rbf_handle h) { return h ? h->last_fit_method : 0; }
 
 int b200rbf_load(b200rbf_handle h, const double* Xu, const double* c, int n, int d, int kernel, int tail) {
   B2_CHECK(h && Xu && c, B200RBF_EINVAL, "NULL argument");
@@ -473,7 +482,46 @@ int b200rbf_fit(b200rbf_handle h, const double* Xu, const double* rhs, int n, in
   B2_TRY(copy_in(h, Xd, Xu, (size_t)n * d * sizeof(double)));
   B2_TRY(copy_in(h, rd, rhs, (size_t)n * sizeof(double)));
   B2_CUDA(cudaEventRecord(h->ev_t0, h->stream));
-  B2_TRY(run_fit(h, Xd, rd, n, d, kernel, tail, eta, cd, info_host));
+  // Null-space Cholesky (fit_chol.cu) where it applies: conditionally positive definite kernel + linear tail, and a
+  // system large enough for the factorisation to matter.  Anything else, and any Cholesky failure, takes the pivoted LU.
+  const bool chol_ok = tail == B200RBF_TAIL_LINEAR && kernel != B200RBF_KERNEL_LINEAR && n >= 2 * t + 32 && t <= 256;
+  B2_CHECK(h->fit_method != 2 || chol_ok, B200RBF_EINVAL,
+           "the Cholesky fit needs a cubic / TPS kernel with the linear tail and n >= 2 ntail + 32");
+  bool done = false;
+  if (chol_ok && (h->fit_method == 2 || (h->fit_method == 0 && n >= 768))) {
+    B2_TRY(h->fit.piv.reserve(256));
+    int* info_dev = h->fit.piv.as<int>();
+    B2_CUDA(cudaMemsetAsync(info_dev, 0, sizeof(int), h->stream));
+    CholWork wk;
+    B2_TRY(chol_fit_weights(h, Xd, rd, n, d, kernel, eta, &wk, info_dev));
+    // (Phi + eta I) c for the tail: evaluate the weights-only model at its own centers with the fused score kernel
+    B2_CUDA(cudaMemsetAsync(cd, 0, (size_t)t * sizeof(double), h->stream));
+    B2_CUDA(cudaMemcpyAsync(cd + t, wk.v2, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    B2_TRY(install_model(h, Xd, cd, n, d, kernel, tail));
+    const int br = block_rows(h->model.dpad);
+    const int np = (n + br - 1) / br + 8;
+    B2_TRY(h->tmp_out.reserve(((size_t)4 * np + n + 16) * sizeof(double)));
+    double* parts = h->tmp_out.as<double>();
+    double* g = parts + (size_t)4 * np;
+    ScorePlan plan;
+    B2_TRY(score_rows(h, plan, Xd, 0, n, nullptr, g, nullptr, parts, np, 0, 0));
+    B2_TRY(chol_fit_tail(h, wk, rd, g, eta, cd));
+    B2_CUDA(cudaMemcpyAsync(info_host, info_dev, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    B2_CUDA(cudaStreamSynchronize(h->stream));
+    if (*info_host == 0) {
+      done = true;
+      h->last_fit_method = 2;
+    } else {
+      B2_CHECK(h->fit_method != 2, B200RBF_ESINGULAR,
+               "Cholesky fit failed (%s step, index %d): projected matrix not numerically positive definite",
+               *info_host < 0 ? "tail QR" : "factorisation", *info_host < 0 ? -*info_host : *info_host);
+      *info_host = 0;  // rbf.py:149-153: a failed Cholesky falls back to a fresh LU
+    }
+  }
+  if (!done) {
+    B2_TRY(run_fit(h, Xd, rd, n, d, kernel, tail, eta, cd, info_host));
+    h->last_fit_method = 1;
+  }
   B2_TRY(install_model(h, Xd, cd, n, d, kernel, tail));
   B2_CUDA(cudaEventRecord(h->ev_t1, h->stream));
   if (c_out) B2_TRY(copy_out(h, c_out, cd, (size_t)N * sizeof(double)));

@@ -161,6 +161,13 @@ struct FitState {
   DevBuf rhs;    // N
   DevBuf work;   // cooperative panel scratch
   DevBuf flags;
+  DevBuf chol;   // workspace of the null-space Cholesky fit (fit_chol.cu)
+};
+
+// views into FitState::chol for one null-space Cholesky fit
+struct CholWork {
+  double *P, *Qneg, *W, *Acat, *Bcat, *T21, *Lt, *G, *R1, *R2, *R, *S, *gpart, *v0, *v1, *v2, *q;
+  int n, n16, t, tp, ld;
 };
 
 }  // namespace b200rbf
@@ -175,6 +182,8 @@ struct b200rbf_ctx {
   // LU look-ahead: panel k+1 factors on a high-priority stream while the rest of trailing update k runs
   cudaStream_t la_stream = nullptr;
   cudaEvent_t ev_la1 = nullptr, ev_la2 = nullptr;
+  int fit_method = 0;  // 0 auto (null-space Cholesky where it applies, else pivoted LU), 1 LU, 2 Cholesky or fail
+  int last_fit_method = 0;  // what the last b200rbf_fit actually used (1 LU, 2 Cholesky)
   bool lu_lookahead = true;
   int gemm_stages = 3;          // cp.async ring depth of the DMMA GEMM
   bool gemm_stages_auto = true; // drop to 2 while a look-ahead panel shares the SMs

@@ -593,6 +593,28 @@ static int gemm_sub(b200rbf_ctx* h, double* C, int ldc, const double* A, int lda
   return gemm_sub_ex(h, C, ldc, A, lda, B, ldb, M, Nc, K, 0);
 }
 
+// Phi + eta I alone (n x n, no tail block), pad columns [n, ncols) zeroed: the operand of the null-space Cholesky fit
+int assemble_plain(b200rbf_ctx* h, const double* Xu_dev, int n, int d, int kernel, double eta, double* A, int ld,
+                   int ncols) {
+  dim3 grid((ncols + kAsmTile - 1) / kAsmTile, (n + kAsmTile - 1) / kAsmTile);
+  if (h->exact_dist)
+    assemble_kernel<true><<<grid, 256, 0, h->stream>>>(Xu_dev, n, d, 0, 0, kernel, eta, nullptr, A, ld, -1, ncols);
+  else
+    assemble_kernel<false><<<grid, 256, 0, h->stream>>>(Xu_dev, n, d, 0, 0, kernel, eta, nullptr, A, ld, -1, ncols);
+  h->launches++;
+  B2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// y[r] -= sum_{c in [c0, c1)} A[r][c] x[c] for rows [r0, r0 + rows)  (one warp per row; shared with fit_chol.cu)
+int strip_gemv(b200rbf_ctx* h, const double* A, int ld, int r0, int rows, int c0, int c1, const double* x, double* y) {
+  if (rows <= 0 || c1 <= c0) return 0;
+  strip_gemv_kernel<<<(rows * 32 + 255) / 256, 256, 0, h->stream>>>(A, ld, r0, rows, c0, c1, x, y);
+  h->launches++;
+  B2_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int lu_factor_device(b200rbf_ctx* h, double* A, int ld, int N, int rcol0, int ncols, int* ipiv, int* info_dev) {
   // blocked right-looking LU of the leading N x N block of the N x ncols row-major matrix.  Columns
   // [rcol0, ncols) (rcol0 even, >= N) ride along as right-hand sides; columns [N, rcol0) are an alignment gap.

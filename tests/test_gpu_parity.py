@@ -444,3 +444,38 @@ def test_mma_and_direct_kernels_agree_on_clustered_points(pb, orc):
         rel = np.abs(dm - tr["dmerit0"].ravel())[50:] / tr["dmerit0"].ravel()[50:]
         assert rel.max() < 1e-9, (mode, rel.max())  # near pairs keep RELATIVE accuracy (direct recomputation)
         assert np.array_equal(idx, tr["picked"]), mode
+
+
+@pytest.mark.parametrize("kernel,d,n", [("cubic", 3, 150), ("tps", 10, 1000), ("cubic", 30, 1500), ("tps", 2, 700)])
+def test_cholesky_fit_matches_lu_and_oracle(pb, orc, kernel, d, n):
+    """The null-space Cholesky solver (fit_chol.cu) against the pivoted LU and the reference's dgetrf path."""
+    from pysot_b200 import _lib
+
+    rng = np.random.default_rng(n + d)
+    lb, ub = -np.ones(d), 2 * np.ones(d)
+    X = lb + (ub - lb) * rng.random((n, d))
+    X[n // 2:] = X[0] + 0.05 * rng.standard_normal((n - n // 2, d))  # half the points clustered (still inside the box)
+    X = np.clip(X, lb, ub)
+    fX = (np.sin(X.sum(1)) + X[:, 0] ** 2)[:, None]
+    q = lb + (ub - lb) * rng.random((300, d))
+    o = orc.OracleRBF(d, lb, ub, kernel, "linear")
+    o.add_points(X, fX)
+    ref_p, ref_g = o.predict(q), o.predict_deriv(q[:10])
+    out = {}
+    for method in (1, 2):
+        s = make_gpu(pb, d, lb, ub, kernel, "linear")
+        s.handle.set_option(_lib.OPT_FIT_METHOD, method)
+        s.add_points(X, fX)
+        out[method] = (s.predict(q), s.predict_deriv(q[:10]), s.c.copy())
+        assert s.handle.last_fit_method == ("lu" if method == 1 else "cholesky")
+        assert relmax(out[method][0], ref_p) < TOL, (method, relmax(out[method][0], ref_p))
+        assert relmax(out[method][1], ref_g) < 1e-9, (method, relmax(out[method][1], ref_g))
+    P = np.hstack((np.ones((n, 1)), (X - lb) / (ub - lb)))
+    c = out[2][2]
+    assert np.max(np.abs(P.T @ c[d + 1:])) < 1e-9 * np.max(np.abs(c))  # the side condition P^T c = 0
+    # linear kernel / constant tail are not conditionally positive definite of order 2: explicit Cholesky is refused
+    s = make_gpu(pb, d, lb, ub, "linear", "constant")
+    s.handle.set_option(_lib.OPT_FIT_METHOD, 2)
+    s.add_points(X, fX)
+    with pytest.raises(ValueError):
+        s.predict(q)
