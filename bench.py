@@ -204,9 +204,12 @@ def fit_benchmark(pb, sizes=(1000, 5000, 20000)):
             best_wall = min(best_wall, time.perf_counter() - t0)
             best_dev = min(best_dev, s.fit_seconds)
         N = n + 11
+        # algorithmic work of the REFERENCE's algorithm (LU of the saddle-point system); the null-space
+        # Cholesky does half of it, so "tflops" below is an equivalent rate, comparable across solvers
         flops = 2.0 / 3.0 * N ** 3 + 2.0 * N ** 2 + 0.5 * n * n * (3 * 10 + 4)
         resid = float(np.max(np.abs(s.predict(X[:2000]) + s.eta * s.c[11:11 + min(n, 2000)] - fX[:2000])))
-        out.append({"n": n, "d": 10, "kernel": "tps", "seconds_device": best_dev, "seconds_host_to_host": best_wall,
+        out.append({"n": n, "d": 10, "kernel": "tps", "solver": s.handle.last_fit_method, "seconds_device": best_dev,
+                    "seconds_host_to_host": best_wall,
                     "tflops": flops / best_dev / 1e12, "interp_residual": resid})
         del s
     return out
@@ -248,7 +251,8 @@ def run_native(args, rank, world, local_rank):
     rbf.add_points(X, fX)
     t0 = time.perf_counter()
     rbf._fit()  # every rank fits its own replica (the fit does not shard: "replicas only")
-    fit50 = {"n": N_CENTERS, "d": D, "kernel": "cubic", "seconds_device": rbf.fit_seconds,
+    fit50 = {"n": N_CENTERS, "d": D, "kernel": "cubic", "solver": rbf.handle.last_fit_method,
+             "seconds_device": rbf.fit_seconds,
              "seconds_host_to_host": time.perf_counter() - t0}
     h = rbf.handle
     Xdist = np.vstack((X, Xpend))

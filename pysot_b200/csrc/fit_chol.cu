@@ -189,37 +189,41 @@ __global__ void pad_identity_kernel(double* __restrict__ A, int ld, int n, int n
   A[(size_t)i * ld + j] = (i == j) ? 1.0 : 0.0;
 }
 
-// Cholesky of the nb x nb diagonal block at (j0, j0) in one CTA; writes L back (lower) and L^T into Lt (nb x kNB)
-__global__ void __launch_bounds__(256) potrf_kernel(double* __restrict__ A, int ld, int j0, int nb,
+// Cholesky of the nb x nb diagonal block at (j0, j0) in one CTA; writes L back (lower) and L^T into Lt (nb x kNB).
+// Right-looking, thread = (row i, column residue mod 8): three barriers per column, conflict-free shared-memory
+// walks (row stride nb + 1), no integer division in the update loop.
+constexpr int kPotrfThreads = 1024, kPotrfParts = kPotrfThreads / kNB;
+__global__ void __launch_bounds__(kPotrfThreads) potrf_kernel(double* __restrict__ A, int ld, int j0, int nb,
                                                     double* __restrict__ Lt, int* __restrict__ info) {
   extern __shared__ double s[];  // nb x (nb + 1)
   const int st = nb + 1, tid = threadIdx.x;
-  for (int e = tid; e < nb * nb; e += blockDim.x) {
-    const int i = e / nb, j = e - i * nb;
-    s[i * st + j] = j <= i ? A[(size_t)(j0 + i) * ld + j0 + j] : 0.0;
-  }
+  const int col = tid & (kNB - 1), half = tid >> 7;  // kNB == 128; `half` = column residue class 0 .. kPotrfParts-1
+  for (int i = half; i < nb; i += kPotrfParts)
+    if (col < nb) s[i * st + col] = col <= i ? A[(size_t)(j0 + i) * ld + j0 + col] : 0.0;
   __syncthreads();
+  const int i = col;  // this thread's row in the update phase
   for (int k = 0; k < nb; ++k) {
-    if (tid == 0) {
+    if (tid == k) {
       const double dgl = s[k * st + k];
       if (!(dgl > 0.0) && *info == 0) *info = j0 + k + 1;
       s[k * st + k] = sqrt(dgl);
     }
     __syncthreads();
-    const double lkk = s[k * st + k];
-    for (int i = k + 1 + tid; i < nb; i += blockDim.x) s[i * st + k] /= lkk;
+    if (half == 0 && i > k && i < nb) s[i * st + k] /= s[k * st + k];
     __syncthreads();
-    const int w = nb - k - 1;
-    for (int e = tid; e < w * w; e += blockDim.x) {
-      const int i = k + 1 + e / w, j = k + 1 + e % w;
-      if (j <= i) s[i * st + j] = fma(-s[i * st + k], s[j * st + k], s[i * st + j]);
+    if (i > k && i < nb) {
+      const double lik = s[i * st + k];
+      for (int j = k + 1 + half; j <= i; j += kPotrfParts) s[i * st + j] = fma(-lik, s[j * st + k], s[i * st + j]);
     }
+    // the next column's pivot s[k+1][k+1] is final once row k+1's own thread(s) are done: the barrier at the top of
+    // the next iteration (after the sqrt by thread k+1) orders it for everyone else
     __syncthreads();
   }
-  for (int e = tid; e < nb * nb; e += blockDim.x) {
-    const int i = e / nb, j = e - i * nb;
-    if (j <= i) A[(size_t)(j0 + i) * ld + j0 + j] = s[i * st + j];
-    Lt[(size_t)j * kNB + i] = j <= i ? s[i * st + j] : 0.0;  // Lt[j][i] = L[i][j]
+  for (int r = half; r < nb; r += kPotrfParts) {
+    if (col < nb) {
+      if (col <= r) A[(size_t)(j0 + r) * ld + j0 + col] = s[r * st + col];
+      Lt[(size_t)r * kNB + col] = col >= r ? s[col * st + r] : 0.0;  // Lt[r][c] = L[c][r]
+    }
   }
 }
 
@@ -258,22 +262,24 @@ __global__ void __launch_bounds__(kNB) diag_lower_solve_kernel(const double* __r
   extern __shared__ double s[];  // rows x (kNB + 1), s[i][k] = L[i][k] (or L^T when transposing)
   __shared__ double sx[kNB];
   const int st = kNB + 1, tid = threadIdx.x;
-  for (int e = tid; e < rows * rows; e += blockDim.x) {
-    const int i = e / rows, k = e - i * rows;
-    const double v = k <= i ? A[(size_t)(r0 + i) * ld + r0 + k] : 0.0;
-    if (transpose) s[k * st + i] = v; else s[i * st + k] = v;
+  for (int i = 0; i < rows; ++i) {  // thread = column: coalesced row reads, no integer division
+    if (tid < rows) {
+      const double e = tid <= i ? A[(size_t)(r0 + i) * ld + r0 + tid] : 0.0;
+      if (transpose) s[tid * st + i] = e; else s[i * st + tid] = e;
+    }
   }
   double v = tid < rows ? y[r0 + tid] : 0.0;
   __syncthreads();
+  const double rdiag = tid < rows ? 1.0 / s[tid * st + tid] : 0.0;  // all reciprocals in parallel, off the critical path
   if (!transpose) {
     for (int k = 0; k < rows; ++k) {
-      if (tid == k) { v = v / s[k * st + k]; sx[k] = v; }
+      if (tid == k) { v *= rdiag; sx[k] = v; }
       __syncthreads();
       if (tid > k && tid < rows) v = fma(-s[tid * st + k], sx[k], v);
     }
   } else {
     for (int k = rows - 1; k >= 0; --k) {
-      if (tid == k) { v = v / s[k * st + k]; sx[k] = v; }
+      if (tid == k) { v *= rdiag; sx[k] = v; }
       __syncthreads();
       if (tid < k) v = fma(-s[tid * st + k], sx[k], v);
     }
@@ -443,7 +449,7 @@ int chol_fit_weights(b200rbf_ctx* h, const double* Xu_dev, const double* f_dev, 
   B2_CUDA(cudaFuncSetAttribute(potrf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_potrf));
   for (int j0 = 0; j0 < n16; j0 += kNB) {
     const int nb = (n16 - j0 < kNB) ? (n16 - j0) : kNB;
-    potrf_kernel<<<1, 256, (size_t)nb * (nb + 1) * sizeof(double), h->stream>>>(A, ld, j0, nb, w.Lt, info_dev);
+    potrf_kernel<<<1, kPotrfThreads, (size_t)nb * (nb + 1) * sizeof(double), h->stream>>>(A, ld, j0, nb, w.Lt, info_dev);
     LAUNCHED(h);
     const int r0 = j0 + nb, rows = n16 - r0;
     if (rows <= 0) break;
@@ -473,11 +479,11 @@ int chol_fit_weights(b200rbf_ctx* h, const double* Xu_dev, const double* f_dev, 
   const size_t sm_diag = (size_t)kNB * (kNB + 1) * sizeof(double);
   B2_CUDA(cudaFuncSetAttribute(diag_lower_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_diag));
   const int nblk = (n16 + kNB - 1) / kNB;
-  for (int b = 0; b < nblk; ++b) {  // forward: L y = b   (y in v1)
+  for (int b = 0; b < nblk; ++b) {  // forward: L y = b   (y in v1), right-looking: every row below updates in parallel
     const int r0 = b * kNB, rows = (n16 - r0 < kNB) ? (n16 - r0) : kNB;
-    B2_TRY(strip_gemv(h, A, ld, r0, rows, 0, r0, w.v1, w.v0));
     diag_lower_solve_kernel<<<1, kNB, sm_diag, h->stream>>>(A, ld, r0, rows, w.v0, w.v1, 0);
     LAUNCHED(h);
+    B2_TRY(strip_gemv(h, A, ld, r0 + rows, n16 - r0 - rows, r0, r0 + rows, w.v1, w.v0));
   }
   for (int b = nblk - 1; b >= 0; --b) {  // backward: L^T x = y   (x in v2, y consumed in v1)
     const int r0 = b * kNB, rows = (n16 - r0 < kNB) ? (n16 - r0) : kNB;
