@@ -122,13 +122,14 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 <= 4 ? kMmaMinBlocks + 1 : kM
   }
 
   const double inf = __longlong_as_double(0x7ff0000000000000LL);
-  double sum[kMmaMB], mn[kMmaMB];
+  double sum[kMmaMB];
+  long long mnb[kMmaMB];  // running min of r^2 as a bit pattern (non-negative doubles order like integers)
 #pragma unroll
   for (int i = 0; i < kMmaMB; ++i) {
     sum[i] = 0.0;
-    mn[i] = inf;
+    mnb[i] = 0x7ff0000000000000LL;
   }
-  const double tau = 0.0009765625;  // 2^-10
+  constexpr long long kNearShift = 10LL << 52;  // near pairs: r^2 < 2^-10 (|u|^2 + |c|^2)
 
   for (int t = 0; t < ntiles; ++t) {
     const int s = t % kMmaStages;
@@ -166,9 +167,12 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 <= 4 ? kMmaMinBlocks + 1 : kM
           for (int e = 0; e < 2; ++e) {
             const double sq = nx[i] + (e ? n2.y : n2.x);
             double r2 = fma(-2.0, acc[i][jb][e], sq);
-            if (r2 < tau * sq)
+            // near test r2 < 2^-10 sq and the running minimum on the INTEGER pipe (the FP64 pipe is the bottleneck):
+            // for non-negative doubles the bit patterns order like the values, 2^-10 sq is sq with its exponent
+            // lowered by 10, and a negative r2 (cancellation) is a negative integer, i.e. below any threshold
+            if (__double_as_longlong(r2) < __double_as_longlong(sq) - kNearShift)
               r2 = mma_exact_r2(a.cand + rows_i[i] * (long long)a.d, a.d, a.lb, a.range, tp + (jc + e) * ds);
-            mn[i] = fmin(mn[i], r2);
+            mnb[i] = min(mnb[i], __double_as_longlong(r2));  // r2 >= 0 here
             sum[i] = fma(rbf_phi_from_r2<KERN>(r2), e ? w2.y : w2.x, sum[i]);
           }
         }
@@ -183,8 +187,8 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 <= 4 ? kMmaMinBlocks + 1 : kM
   for (int i = 0; i < kMmaMB; ++i) {
     sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], 1);
     sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], 2);
-    mn[i] = fmin(mn[i], __shfl_xor_sync(0xffffffffu, mn[i], 1));
-    mn[i] = fmin(mn[i], __shfl_xor_sync(0xffffffffu, mn[i], 2));
+    mnb[i] = min(mnb[i], __shfl_xor_sync(0xffffffffu, mnb[i], 1));
+    mnb[i] = min(mnb[i], __shfl_xor_sync(0xffffffffu, mnb[i], 2));
   }
   // tail: lambda_0 + sum_k lambda_k u_k over this thread's dimensions, then across the quad
   double fmn = inf, fmx = -inf, dmn = inf, dmx = -inf;
@@ -204,7 +208,7 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 <= 4 ? kMmaMinBlocks + 1 : kM
     const bool live = row < a.m;
     const double fval = sum[i] + (ts + __ldg(a.tailc));
     double dval = 0.0;
-    if (a.min_mode != 0) dval = a.dscale * sqrt(mn[i]);
+    if (a.min_mode != 0) dval = a.dscale * sqrt(__longlong_as_double(mnb[i]));
     if (live && tig == 0) {
       a.fvals[row] = fval;
       if (a.min_mode != 0) {
