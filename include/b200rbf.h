@@ -118,6 +118,17 @@ int b200rbf_score(b200rbf_handle h, const double* cand, long long m, const doubl
 int b200rbf_select(b200rbf_handle h, const double* weights, int p, double dtol, long long* idx_out,
                    double* merit_out);
 
+/* Candidate generation on the device (opt-in; candidate_dycors.py:73-86, candidate_srbf.py:108-113,
+ * candidate_uniform.py:44-45, round_vars utils.py:68-93).  kind: 0 DYCORS, 1 SRBF, 2 uniform.  xbest, lb, ub, sigma
+ * (= sampling_radius * (ub - lb), at least 1 for integer variables): d HOST doubles; subset: nsub coordinate indices
+ * or NULL for all; int_mask: d bytes flagging integer variables or NULL; cand_dev: m x d DEVICE buffer.  Philox4x32-10
+ * keyed by (seed, row, coordinate): same seed -> same candidates, but NOT numpy's / scipy's streams, so seeded runs do
+ * not reproduce the reference's candidate sets (their distribution is identical).  The launch is asynchronous on the
+ * handle's stream. */
+int b200rbf_generate(b200rbf_handle h, int kind, long long m, int d, const double* xbest, const double* lb,
+                     const double* ub, const double* sigma, double prob_perturb, const int* subset, int nsub,
+                     const unsigned char* int_mask, unsigned long long seed, double* cand_dev);
+
 /* ---- phase API for candidates sharded over several GPUs (one process and one handle per GPU).  The
  * caller reduces the tiny device buffers between phases with NCCL (torch.distributed):
  *   stats_dev  : 4 doubles {fmin, -fmax, dmin, -dmax}  -> all-reduce(MIN)

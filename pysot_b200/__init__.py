@@ -14,8 +14,8 @@ from .interface import (  # noqa: F401
 )
 from .rbf import GpuRBFInterpolant  # noqa: F401
 from .candidates import (  # noqa: F401
-    candidate_dycors, candidate_srbf, candidate_uniform, generate_dycors, generate_srbf, generate_uniform, install,
-    merit_select_indices, uninstall, weighted_distance_merit,
+    candidate_dycors, candidate_srbf, candidate_uniform, generate_dycors, generate_on_device, generate_srbf,
+    generate_uniform, install, merit_select_indices, set_candidate_generator, uninstall, weighted_distance_merit,
 )
 
 __version__ = "0.1.0"

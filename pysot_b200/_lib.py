@@ -32,6 +32,8 @@ PROTOTYPES = {
     "b200rbf_predict_deriv": (C.c_int, [_vp, _vp, C.c_longlong, _vp, _vp, _vp]),
     "b200rbf_score": (C.c_int, [_vp, _vp, C.c_longlong, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "b200rbf_select": (C.c_int, [_vp, _vp, C.c_int, C.c_double, _vp, _vp]),
+    "b200rbf_generate": (C.c_int, [_vp, C.c_int, C.c_longlong, C.c_int, _vp, _vp, _vp, _vp, C.c_double, _vp, C.c_int, _vp,
+                                   C.c_ulonglong, _vp]),
     "b200rbf_shard_stats": (C.c_int, [_vp, _vp]),
     "b200rbf_shard_argmin": (C.c_int, [_vp, C.c_double, C.c_double, _vp, C.c_longlong, _vp]),
     "b200rbf_shard_take": (C.c_int, [_vp, C.c_longlong, _vp]),
@@ -198,6 +200,20 @@ class Handle:
         merit = np.empty(num_pts)
         check(load().b200rbf_select(self._h, ptr(w), int(num_pts), float(dtol), ptr(idx), ptr(merit)))
         return idx, merit
+
+    def generate(self, kind, m, xbest, lb, ub, sigma, prob_perturb, subset, int_var, seed, cand_dev):
+        """Fill the CUDA tensor cand_dev (m, d) with candidates; kind in {"dycors", "srbf", "uniform"}."""
+        xbest, lb, ub = f64(xbest), f64(lb), f64(ub)
+        d = xbest.shape[0]
+        sigma = f64(sigma) if sigma is not None else None
+        sub = np.ascontiguousarray(subset, dtype=np.int32) if subset is not None else None
+        mask = None
+        if int_var is not None and len(int_var) > 0:
+            mask = np.zeros(d, dtype=np.uint8)
+            mask[np.asarray(int_var, dtype=int)] = 1
+        check(load().b200rbf_generate(self._h, {"dycors": 0, "srbf": 1, "uniform": 2}[kind], int(m), d, ptr(xbest), ptr(lb),
+                                      ptr(ub), ptr(sigma), float(prob_perturb), ptr(sub), 0 if sub is None else len(sub),
+                                      ptr(mask), int(seed) & 0xFFFFFFFFFFFFFFFF, ptr(cand_dev)))
 
     # ---- sharded phases (device pointers: torch CUDA tensors)
     def shard_stats(self, stats_dev):

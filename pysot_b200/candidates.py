@@ -29,15 +29,24 @@ def _round_vars(x, int_var, lb, ub):
     return x
 
 
+def _is_cuda_tensor(a):
+    return hasattr(a, "is_cuda") and a.is_cuda
+
+
 def weighted_distance_merit(num_pts, surrogate, X, fX, cand, weights, Xpend=None, dtol=1e-3):
     """Pick ``num_pts`` rows of ``cand`` by the weighted-distance merit (candidate_srbf.py:8-57).
 
-    Returns a ``(num_pts, dim)`` float64 array of rows copied from ``cand``.
+    ``cand`` is a host array or (tensor hand-off) a contiguous float64 CUDA tensor.  Returns a ``(num_pts, dim)``
+    float64 numpy array of rows copied from ``cand``.
     """
     if not isinstance(surrogate, GpuRBFInterpolant):
         raise TypeError("pysot_b200.weighted_distance_merit needs a GpuRBFInterpolant (there is no CPU fallback); got %r"
                         % type(surrogate).__name__)
     idx = merit_select_indices(num_pts, surrogate, X, cand, weights, Xpend, dtol)[0]
+    if _is_cuda_tensor(cand):
+        import torch
+
+        return cand[torch.as_tensor(idx, device=cand.device)].cpu().numpy()
     return np.asarray(cand, dtype=np.float64)[idx, :].copy()
 
 
@@ -45,7 +54,12 @@ def merit_select_indices(num_pts, surrogate, X, cand, weights, Xpend=None, dtol=
     """The device part of weighted_distance_merit.  Returns (indices, merit values[, fvals, dmerit, stats])."""
     X = np.asarray(X, dtype=np.float64)
     dim = X.shape[1]
-    cand = np.asarray(cand, dtype=np.float64)
+    if _is_cuda_tensor(cand):
+        import torch
+
+        assert cand.dtype == torch.float64 and cand.is_contiguous()
+    else:
+        cand = np.asarray(cand, dtype=np.float64)
     if cand.ndim != 2 or cand.shape[1] != dim:
         raise ValueError("XA and XB must have the same number of columns (i.e. feature dimension.)")  # cdist's message
     if Xpend is None:
@@ -58,11 +72,41 @@ def merit_select_indices(num_pts, surrogate, X, cand, weights, Xpend=None, dtol=
     # distance serves both metrics.  extra_points (surrogate_strategy.py:243-247) break the aliasing.
     alias = X.shape == surrogate.X.shape and np.array_equal(X, surrogate.X)
     h = surrogate.handle
-    fv, dm, st = h.score(cand, surrogate.lb, surrogate.ub, Xdist, alias, want_scores=want_scores)
+    fv, dm, st = h.score(cand, surrogate.lb, surrogate.ub, Xdist, alias, want_scores=want_scores, m=cand.shape[0])
     idx, merit = h.select(weights, num_pts, dtol)
     if want_scores:
         return idx, merit, fv, dm, st
     return idx, merit
+
+
+# ------------------------------------------------------------------------------------------ where candidates are drawn
+_GENERATOR = {"mode": "host", "seed": 0, "calls": 0}
+
+
+def set_candidate_generator(mode="host", seed=0):
+    """``"host"`` (default): numpy / scipy draws in the reference's exact call order -- seeded runs reproduce the
+    reference's candidate sets.  ``"device"``: candidates are drawn on the GPU (Philox, `b200rbf_generate`) and never
+    touch the host; same distributions, different streams.  Every call uses a fresh sub-stream
+    of ``seed``."""
+    if mode not in ("host", "device"):
+        raise ValueError("mode must be 'host' or 'device'")
+    _GENERATOR.update(mode=mode, seed=int(seed), calls=0)
+
+
+def generate_on_device(kind, opt_prob, surrogate, X, fX, prob_perturb=1.0, sampling_radius=0.2, subset=None,
+                       num_cand=None, xbest=None, seed=None):
+    """Draw the candidate set of candidate_{dycors,srbf,uniform} on the surrogate's GPU; returns a CUDA tensor."""
+    import torch
+
+    xbest, num_cand, subset = _prepare(opt_prob, X, fX, subset, num_cand, xbest)
+    sigma = None if kind == "uniform" else _scale_factors(opt_prob, sampling_radius, subset)
+    if seed is None:
+        seed = (_GENERATOR["seed"] * 0x9E3779B97F4A7C15 + _GENERATOR["calls"] * 0xD1B54A32D192ED03 + 1) & 0xFFFFFFFFFFFFFFFF
+        _GENERATOR["calls"] += 1
+    cand = torch.empty((int(num_cand), opt_prob.dim), dtype=torch.float64, device=torch.device("cuda", surrogate._device))
+    surrogate.handle.generate(kind, int(num_cand), xbest, opt_prob.lb, opt_prob.ub, sigma, prob_perturb,
+                              np.asarray(subset, dtype=np.int32), opt_prob.int_var, seed, cand)
+    return cand
 
 
 def _prepare(opt_prob, X, fX, subset, num_cand, xbest=None):
@@ -129,7 +173,10 @@ def generate_uniform(opt_prob, X, fX, subset=None, num_cand=None):
 def candidate_srbf(num_pts, opt_prob, surrogate, X, fX, weights, Xpend=None, sampling_radius=0.2, subset=None,
                    dtol=1e-3, num_cand=None):
     """candidate_srbf.py:60-121."""
-    cand = generate_srbf(opt_prob, X, fX, sampling_radius, subset, num_cand)
+    if _GENERATOR["mode"] == "device":
+        cand = generate_on_device("srbf", opt_prob, surrogate, X, fX, 1.0, sampling_radius, subset, num_cand)
+    else:
+        cand = generate_srbf(opt_prob, X, fX, sampling_radius, subset, num_cand)
     return weighted_distance_merit(num_pts=num_pts, surrogate=surrogate, X=X, fX=fX, Xpend=Xpend, cand=cand,
                                    dtol=dtol, weights=weights)
 
@@ -137,7 +184,11 @@ def candidate_srbf(num_pts, opt_prob, surrogate, X, fX, weights, Xpend=None, sam
 def candidate_dycors(num_pts, opt_prob, surrogate, X, fX, weights, prob_perturb, Xpend=None, sampling_radius=0.2,
                      subset=None, dtol=1e-3, num_cand=None, xbest=None):
     """candidate_dycors.py:8-94."""
-    cand = generate_dycors(opt_prob, X, fX, prob_perturb, sampling_radius, subset, num_cand, xbest)
+    if _GENERATOR["mode"] == "device":
+        cand = generate_on_device("dycors", opt_prob, surrogate, X, fX, prob_perturb, sampling_radius, subset, num_cand,
+                                  xbest)
+    else:
+        cand = generate_dycors(opt_prob, X, fX, prob_perturb, sampling_radius, subset, num_cand, xbest)
     return weighted_distance_merit(num_pts=num_pts, surrogate=surrogate, X=X, fX=fX, Xpend=Xpend, cand=cand,
                                    dtol=dtol, weights=weights)
 
@@ -145,7 +196,10 @@ def candidate_dycors(num_pts, opt_prob, surrogate, X, fX, weights, prob_perturb,
 def candidate_uniform(num_pts, opt_prob, surrogate, X, fX, weights, Xpend=None, subset=None, dtol=1e-3,
                       num_cand=None):
     """candidate_uniform.py:7-53."""
-    cand = generate_uniform(opt_prob, X, fX, subset, num_cand)
+    if _GENERATOR["mode"] == "device":
+        cand = generate_on_device("uniform", opt_prob, surrogate, X, fX, 1.0, 0.2, subset, num_cand)
+    else:
+        cand = generate_uniform(opt_prob, X, fX, subset, num_cand)
     return weighted_distance_merit(num_pts=num_pts, surrogate=surrogate, X=X, fX=fX, Xpend=Xpend, cand=cand,
                                    dtol=dtol, weights=weights)
 

@@ -18,6 +18,9 @@ int chol_fit_weights(b200rbf_ctx* h, const double* Xu_dev, const double* f_dev, 
                      CholWork* wk, int* info_dev);
 int chol_fit_tail(b200rbf_ctx* h, const CholWork& w, const double* f_dev, const double* g_dev, double eta,
                   double* c_full_dev);
+int run_generate(b200rbf_ctx* h, int kind, long long m, int d, const double* xbest, const double* lb, const double* ub,
+                 const double* sigma, double prob_perturb, const int* subset, int nsub, const unsigned char* int_mask,
+                 unsigned long long seed, double* cand_dev);
 int run_lu_debug(b200rbf_ctx* h, double* A_dev, int ld, int N, int rcol0, int ncols, int* ipiv_dev, int* info_dev);
 int run_gemm_debug(b200rbf_ctx* h, double* C, int ldc, const double* A, int lda, const double* B, int ldb, int M,
                    int Nc, int K);
@@ -396,7 +399,7 @@ int b200rbf_destroy(b200rbf_handle h) {
   S.stats.release(); S.winner.release(); S.results.release(); S.dist.release(); S.box.release();
   FitState& F = h->fit;
   F.A.release(); F.piv.release(); F.rhs.release(); F.work.release(); F.flags.release(); F.chol.release();
-  h->tmp_in.release(); h->tmp_out.release(); h->tmp_box.release();
+  h->tmp_in.release(); h->tmp_out.release(); h->tmp_box.release(); h->gen_buf.release(); h->gen_pin.release();
   h->stage[0].release(); h->stage[1].release(); h->pin_small.release();
   for (int i = 0; i < 2; ++i) cudaEventDestroy(h->ev_copy[i]);
   cudaEventDestroy(h->ev_t0); cudaEventDestroy(h->ev_t1); cudaEventDestroy(h->ev_done);
@@ -753,6 +756,31 @@ int b200rbf_shard_update(b200rbf_handle h, const double* winner_dev) {
                        h->exact_dist));
   B2_TRY(launch_stats(h, S.parts.as<double>(), S.nparts, cnt, 2, S.stats.as<double>()));
   return 0;
+}
+
+int b200rbf_generate(b200rbf_handle h, int kind, long long m, int d, const double* xbest, const double* lb,
+                     const double* ub, const double* sigma, double prob_perturb, const int* subset, int nsub,
+                     const unsigned char* int_mask, unsigned long long seed, double* cand_dev) {
+  B2_CHECK(h && xbest && lb && ub && cand_dev, B200RBF_EINVAL, "NULL argument");
+  B2_CHECK(kind >= 0 && kind <= 2, B200RBF_EINVAL, "unknown generator kind %d", kind);
+  B2_CHECK(m >= 1 && d >= 1, B200RBF_EINVAL, "m and d must be positive");
+  B2_CHECK(kind == 2 || sigma != nullptr, B200RBF_EINVAL, "sigma is required for the truncated-normal generators");
+  B2_CHECK(ptr_kind(cand_dev) == kDevice, B200RBF_EINVAL, "cand_dev must be device memory");
+  if (subset == nullptr) nsub = d;
+  B2_CHECK(nsub >= 1 && nsub <= d, B200RBF_EINVAL, "subset size %d out of range", nsub);
+  for (int j = 0; subset && j < nsub; ++j)
+    B2_CHECK(subset[j] >= 0 && subset[j] < d, B200RBF_EINVAL, "subset index %d out of range", subset[j]);
+  for (int k = 0; k < d; ++k) {
+    B2_CHECK(lb[k] <= xbest[k] && xbest[k] <= ub[k], B200RBF_EINVAL, "xbest[%d] outside [lb, ub]", k);
+    B2_CHECK(kind == 2 || sigma[k] > 0.0, B200RBF_EINVAL, "sigma[%d] must be positive", k);
+  }
+  B2_CUDA(cudaSetDevice(h->device));
+  std::vector<double> ones;
+  if (sigma == nullptr) {
+    ones.assign(d, 1.0);
+    sigma = ones.data();
+  }
+  return run_generate(h, kind, m, d, xbest, lb, ub, sigma, prob_perturb, subset, nsub, int_mask, seed, cand_dev);
 }
 
 int b200rbf_fp64_peaks(b200rbf_handle h, double ms, double* out) {

@@ -198,6 +198,8 @@ struct b200rbf_ctx {
   b200rbf::ScoreState score;
   b200rbf::FitState fit;
   b200rbf::DevBuf tmp_in, tmp_out, tmp_box;
+  b200rbf::DevBuf gen_buf;  // parameters of the candidate generator
+  b200rbf::PinBuf gen_pin;
 };
 
 namespace b200rbf {
