@@ -57,7 +57,7 @@ enum {
    *    tensor path and a direct recomputation of near pairs (score_mma.cuh; ~1.6x fewer FP64 cycles at d = 50,
    *    relative error of r^2 <= ~1e-12).  0: direct differences everywhere.  Ignored when EXACT_DIST is set.     */
   B200RBF_OPT_MMA_DIST = 6,
-  /* solver of b200rbf_fit: 0 (default) auto = null-space Cholesky for cubic / TPS + linear tail with n >= 768, pivoted
+  /* solver of b200rbf_fit: 0 (default) auto = null-space Cholesky for cubic / TPS + linear tail with n >= 128, pivoted
    *    LU otherwise and whenever the Cholesky reports a non-positive pivot; 1 = always LU; 2 = Cholesky or error       */
   B200RBF_OPT_FIT_METHOD = 7
 };

@@ -491,7 +491,7 @@ int b200rbf_fit(b200rbf_handle h, const double* Xu, const double* rhs, int n, in
   B2_CHECK(h->fit_method != 2 || chol_ok, B200RBF_EINVAL,
            "the Cholesky fit needs a cubic / TPS kernel with the linear tail and n >= 2 ntail + 32");
   bool done = false;
-  if (chol_ok && (h->fit_method == 2 || (h->fit_method == 0 && n >= 768))) {
+  if (chol_ok && (h->fit_method == 2 || (h->fit_method == 0 && n >= 128))) {
     B2_TRY(h->fit.piv.reserve(256));
     int* info_dev = h->fit.piv.as<int>();
     B2_CUDA(cudaMemsetAsync(info_dev, 0, sizeof(int), h->stream));
