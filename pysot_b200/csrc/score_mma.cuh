@@ -30,11 +30,17 @@ namespace b200rbf {
 #endif
 constexpr int kMmaThreads = 128;           // 4 warps
 constexpr int kMmaMB = B2_MMA_MB;          // m8 candidate blocks per warp (A fragments held in registers)
-constexpr int kMmaJB = 4;                  // n8 center blocks per step (32 centers = one tile)
+#ifndef B2_MMA_JB
+#define B2_MMA_JB 4
+#endif
+constexpr int kMmaJB = B2_MMA_JB;          // n8 center blocks per step (8 * JB centers = one tile)
 constexpr int kMmaMinBlocks = B2_MMA_MINB; // CTAs per SM the register budget is capped for (+1 when d <= 16);
                                            // tools/k2x_tune.cu sweep: 2 x 4 beats 2 x 3 by 6 %, 4 x 2 by 16 % at d = 50
 constexpr int kMmaTileRows = 8 * kMmaJB;   // center rows per tile
-constexpr int kMmaStages = 3;
+#ifndef B2_MMA_STAGES
+#define B2_MMA_STAGES 3
+#endif
+constexpr int kMmaStages = B2_MMA_STAGES;
 constexpr int kMmaRowsPerCta = (kMmaThreads / 32) * 8 * kMmaMB;
 
 struct MmaArgs {

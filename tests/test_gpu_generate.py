@@ -114,3 +114,38 @@ def test_selection_on_device_generated_candidates_matches_oracle():
             assert pts.shape == (2, prob.dim) and np.all(pts >= prob.lb) and np.all(pts <= prob.ub)
     finally:
         pb.set_candidate_generator("host")
+
+
+def test_sixteen_million_device_generated_candidates():
+    """BASELINE config #4's upper range on one GPU without the host: 2^24 candidates (6.7 GB) are drawn, scored against
+    2 000 centers and selected on the device; size-independent properties are checked with torch on the same tensors."""
+    import torch
+
+    import pysot_b200 as pb
+
+    rng = np.random.default_rng(0)
+    d, n, m = 50, 2000, 1 << 24
+    prob = Problem(np.zeros(d), np.ones(d))
+    X = rng.random((n, d))
+    fX = (np.sin(3 * X.sum(1)) + X[:, 0] ** 2)[:, None]
+    s = pb.GpuRBFInterpolant(dim=d, lb=prob.lb, ub=prob.ub)
+    s.add_points(X, fX)
+    cand = pb.generate_on_device("dycors", prob, s, X, fX, prob_perturb=0.4, num_cand=m, seed=5)
+    assert cand.shape == (m, d) and float(cand.min()) >= 0.0 and float(cand.max()) <= 1.0
+    idx, merit, fv, dm, st = pb.merit_select_indices(4, s, X, cand, [0.3, 0.5, 0.8, 0.95], None, want_scores=True)
+    assert len(set(idx.tolist())) == 4 and idx.min() >= 0 and idx.max() < m
+    assert st[0] == fv.min() and st[1] == fv.max() and st[2] == dm.min() and st[3] == dm.max()
+    # spot-check rows from the far end of the index range against a torch fp64 evaluation of the same formula
+    rows = torch.tensor([0, 1, m // 2, m - 2, m - 1] + idx.tolist(), device=cand.device)
+    Xt = torch.from_numpy(X).to(cand.device)
+    r = torch.cdist(cand[rows], Xt)
+    c = torch.from_numpy(s.c).to(cand.device)
+    ref_f = (r ** 3) @ c[d + 1:] + c[0] + cand[rows] @ c[1:d + 1]
+    ref_d = r.min(dim=1).values
+    got_f = torch.from_numpy(fv)[rows.cpu()]
+    got_d = torch.from_numpy(dm)[rows.cpu()]
+    assert float((ref_f.cpu().ravel() - got_f).abs().max()) < 1e-9 * float(ref_f.abs().max())
+    assert float((ref_d.cpu() - got_d).abs().max()) < 1e-12
+    # every pick is at least dtol away from every evaluated point and from the earlier picks
+    P = cand[torch.as_tensor(idx, device=cand.device)]
+    assert float(torch.cdist(P, Xt).min()) >= 1e-3 and float(torch.pdist(P).min()) >= 1e-3
