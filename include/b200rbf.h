@@ -49,9 +49,10 @@ enum {
   B200RBF_OPT_CHUNK_ROWS = 2,
   /* LU panel width (default 128; multiple of 32)                                                       */
   B200RBF_OPT_LU_PANEL = 3,
-  /* 1 (default): factor panel k+1 on a second, high-priority stream while the rest of trailing update k runs  */
+  /* 1: factor panel k+1 on a second, high-priority stream while the rest of trailing update k runs.  Default 0:
+   *    measured to give no overlap (two GEMM CTAs fill an SM's registers), so the LU keeps cooperative launches  */
   B200RBF_OPT_LU_LOOKAHEAD = 4,
-  /* cp.async ring depth of the DMMA GEMM: 2, 3, or 0 = auto (2 while a look-ahead panel shares the SMs, else 3) */
+  /* DMMA GEMM variant: 2 or 3 = cp.async stages at BK 16, 4 = 2 stages at BK 32; 0 = auto (4; 2 under LU look-ahead) */
   B200RBF_OPT_GEMM_STAGES = 5,
   /* 1 (default): surrogate values use the norm expansion |u|^2 + |c|^2 - 2 u.c with the dot products on the FP64
    *    tensor path and a direct recomputation of near pairs (score_mma.cuh; ~1.6x fewer FP64 cycles at d = 50,

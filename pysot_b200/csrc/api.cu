@@ -434,9 +434,9 @@ int b200rbf_set_option(b200rbf_handle h, int option, long long value) {
       return 0;
     case B200RBF_OPT_LU_LOOKAHEAD: h->lu_lookahead = value != 0; return 0;
     case B200RBF_OPT_GEMM_STAGES:
-      B2_CHECK(value == 0 || value == 2 || value == 3, B200RBF_EINVAL, "GEMM stages must be 0 (auto), 2 or 3");
+      B2_CHECK(value == 0 || (value >= 2 && value <= 4), B200RBF_EINVAL, "GEMM variant must be 0 (auto), 2, 3 or 4");
       h->gemm_stages_auto = value == 0;
-      h->gemm_stages = value == 0 ? 3 : (int)value;
+      h->gemm_stages = value == 0 ? 4 : (int)value;
       return 0;
     case B200RBF_OPT_LU_PANEL:
       B2_CHECK(value >= 32 && value <= 128 && value % 32 == 0, B200RBF_EINVAL, "LU panel must be 32, 64, 96 or 128");

@@ -184,8 +184,8 @@ struct b200rbf_ctx {
   cudaEvent_t ev_la1 = nullptr, ev_la2 = nullptr;
   int fit_method = 0;  // 0 auto (null-space Cholesky where it applies, else pivoted LU), 1 LU, 2 Cholesky or fail
   int last_fit_method = 0;  // what the last b200rbf_fit actually used (1 LU, 2 Cholesky)
-  bool lu_lookahead = true;
-  int gemm_stages = 3;          // cp.async ring depth of the DMMA GEMM
+  bool lu_lookahead = false;  // implemented and correct, but measured to give no overlap (see include/b200rbf.h)
+  int gemm_stages = 4;          // DMMA GEMM variant: 2 / 3 = cp.async stages at BK 16, 4 = 2 stages at BK 32 (default)
   bool gemm_stages_auto = true; // drop to 2 while a look-ahead panel shares the SMs
   b200rbf::PinBuf stage[2];
   b200rbf::PinBuf pin_small;

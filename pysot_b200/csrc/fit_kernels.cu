@@ -330,11 +330,11 @@ __global__ void __launch_bounds__(128) trsm32_kernel(double* __restrict__ A, int
 // Operands stream through a 3-stage cp.async ring with ONE barrier per k-step.  The C tile is loaded into the
 // accumulators up front (its latency hides behind the first k-steps) and A fragments are negated on the way in,
 // so acc = C - A B accumulates directly and the epilogue is store-only.
-constexpr int kGemmBM = 128, kGemmBN = 64, kGemmBK = 16, kGemmThreads = 256;
-constexpr int kGemmLdA = kGemmBK + 4;   // 20 doubles: 4 consecutive rows x 4 k hit 16 distinct bank pairs
+constexpr int kGemmBM = 128, kGemmBN = 64, kGemmThreads = 256;  // BK (16 or 32) is a template parameter
+template <int BK> __host__ __device__ constexpr int gemm_lda() { return BK + 4; }  // 20 / 36 doubles (== 4 mod 16): conflict-free A fragments
 constexpr int kGemmLdB = kGemmBN + 4;   // 68 doubles (68 mod 16 == 4): same for 4 k x 4 columns
-constexpr int kGemmStageDoubles = kGemmBM * kGemmLdA + kGemmBK * kGemmLdB;
-constexpr size_t gemm_smem_bytes(int stages) { return (size_t)stages * kGemmStageDoubles * sizeof(double); }
+template <int BK> __host__ __device__ constexpr int gemm_stage_doubles() { return kGemmBM * gemm_lda<BK>() + BK * kGemmLdB; }
+template <int BK> constexpr size_t gemm_smem_bytes(int stages) { return (size_t)stages * gemm_stage_doubles<BK>() * sizeof(double); }
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem)
@@ -350,12 +350,13 @@ __device__ __forceinline__ void dmma_884(double& d0, double& d1, double a, doubl
                : "d"(a), "d"(b));
 }
 
-template <int kGemmStages>
+template <int kGemmStages, int kGemmBK>
 __global__ void __launch_bounds__(kGemmThreads, 2) gemm_sub_kernel(double* __restrict__ C, int ldc,
                                                                    const double* __restrict__ A, int lda,
                                                                    const double* __restrict__ B, int ldb, int M,
                                                                    int Nc, int K, int lower) {
   extern __shared__ __align__(16) double gsm[];
+  constexpr int kGemmLdA = gemm_lda<kGemmBK>(), kGemmStageDoubles = gemm_stage_doubles<kGemmBK>();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 1, wn = warp & 1;  // 4 x 2 warps, warp tile 32 x 32
   const int m0 = blockIdx.y * kGemmBM, n0 = blockIdx.x * kGemmBN;
@@ -367,15 +368,15 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_sub_kernel(double* __res
     double* sB = sA + kGemmBM * kGemmLdA;
     // A tile: 128 rows x 16 k = 128 x 8 chunks of 16 B; rows clamped (results of clamped rows are discarded)
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
+    for (int it = 0; it < kGemmBK / 4; ++it) {  // 128 rows x BK/2 chunks of 16 B
       const int e = tid + it * kGemmThreads;
-      const int r = e >> 3, ch = e & 7;
+      const int r = e / (kGemmBK / 2), ch = e % (kGemmBK / 2);
       const int gr = min(m0 + r, M - 1);
       cp_async16(sA + r * kGemmLdA + ch * 2, A + (size_t)gr * lda + k0 + ch * 2);
     }
     // B tile: 16 k x 64 columns = 16 x 32 chunks; columns past Nc are clamped into the row (results discarded)
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
+    for (int it = 0; it < kGemmBK / 8; ++it) {  // BK rows x 32 chunks
       const int e = tid + it * kGemmThreads;
       const int r = e >> 5, ch = e & 31;
       int gc = n0 + ch * 2;
@@ -562,19 +563,19 @@ __global__ void __launch_bounds__(256) dmix_peak_kernel(double* out, int iters, 
 }  // namespace
 
 // =================================================================================================== host side
-template <int STAGES>
+template <int STAGES, int BK>
 static int gemm_sub_inst(b200rbf_ctx* h, double* C, int ldc, const double* A, int lda, const double* B, int ldb, int M,
                          int Nc, int K, int lower) {
   static bool attr = false;
-  constexpr size_t smem = gemm_smem_bytes(STAGES);
+  constexpr size_t smem = gemm_smem_bytes<BK>(STAGES);
   if (!attr) {
-    B2_CUDA(cudaFuncSetAttribute(gemm_sub_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    B2_CUDA(cudaFuncSetAttribute(gemm_sub_kernel<STAGES>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    B2_CUDA(cudaFuncSetAttribute(gemm_sub_kernel<STAGES, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2_CUDA(cudaFuncSetAttribute(gemm_sub_kernel<STAGES, BK>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  (int)cudaSharedmemCarveoutMaxShared));
     attr = true;
   }
   dim3 grid((Nc + kGemmBN - 1) / kGemmBN, (M + kGemmBM - 1) / kGemmBM);
-  gemm_sub_kernel<STAGES><<<grid, kGemmThreads, smem, h->stream>>>(C, ldc, A, lda, B, ldb, M, Nc, K, lower);
+  gemm_sub_kernel<STAGES, BK><<<grid, kGemmThreads, smem, h->stream>>>(C, ldc, A, lda, B, ldb, M, Nc, K, lower);
   h->launches++;
   B2_CUDA(cudaGetLastError());
   return 0;
@@ -584,9 +585,11 @@ static int gemm_sub_inst(b200rbf_ctx* h, double* C, int ldc, const double* A, in
 int gemm_sub_ex(b200rbf_ctx* h, double* C, int ldc, const double* A, int lda, const double* B, int ldb, int M, int Nc,
                 int K, int lower) {
   if (M <= 0 || Nc <= 0 || K <= 0) return 0;
-  // 2 stages (58 KB) leave room for a look-ahead panel CTA beside one GEMM CTA on the same SM; 3 stages otherwise
-  return h->gemm_stages == 2 ? gemm_sub_inst<2>(h, C, ldc, A, lda, B, ldb, M, Nc, K, lower)
-                             : gemm_sub_inst<3>(h, C, ldc, A, lda, B, ldb, M, Nc, K, lower);
+  // gemm_stages: 2 = 2-stage BK 16 (58 KB: leaves room for a look-ahead panel CTA), 3 = 3-stage BK 16,
+  // 4 = 2-stage BK 32 (109 KB, half the barriers) when K allows it
+  if (h->gemm_stages == 4 && K % 32 == 0) return gemm_sub_inst<2, 32>(h, C, ldc, A, lda, B, ldb, M, Nc, K, lower);
+  return h->gemm_stages == 2 ? gemm_sub_inst<2, 16>(h, C, ldc, A, lda, B, ldb, M, Nc, K, lower)
+                             : gemm_sub_inst<3, 16>(h, C, ldc, A, lda, B, ldb, M, Nc, K, lower);
 }
 static int gemm_sub(b200rbf_ctx* h, double* C, int ldc, const double* A, int lda, const double* B, int ldb, int M,
                     int Nc, int K) {

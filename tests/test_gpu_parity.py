@@ -479,3 +479,26 @@ def test_cholesky_fit_matches_lu_and_oracle(pb, orc, kernel, d, n):
     s.add_points(X, fX)
     with pytest.raises(ValueError):
         s.predict(q)
+
+
+def test_lu_lookahead_and_gemm_variants_give_identical_coefficients(pb):
+    """The optional LU look-ahead stream and the three DMMA GEMM variants reorder launches / tiles, not arithmetic."""
+    from pysot_b200 import _lib
+
+    rng = np.random.default_rng(9)
+    d, n = 6, 900
+    X = rng.random((n, d))
+    fX = np.cos(2 * X.sum(1))[:, None]
+    ref = None
+    for look, variant, method in [(0, 3, 1), (1, 0, 1), (0, 2, 1), (0, 4, 1), (0, 3, 2), (0, 4, 2)]:
+        s = make_gpu(pb, d, np.zeros(d), np.ones(d), "cubic", "linear")
+        s.handle.set_option(_lib.OPT_LU_LOOKAHEAD, look)
+        s.handle.set_option(_lib.OPT_GEMM_STAGES, variant)
+        s.handle.set_option(_lib.OPT_FIT_METHOD, method)
+        s.add_points(X, fX)
+        s._fit()
+        if method == 1:
+            ref = s.c.copy() if ref is None else ref
+            assert np.array_equal(s.c, ref), (look, variant)  # same products, same order within each accumulator
+        else:
+            assert relmax(s.c, ref) < 1e-7  # different algorithm: coefficients agree to cond * eps
