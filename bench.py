@@ -208,9 +208,20 @@ def fit_benchmark(pb, sizes=(1000, 5000, 20000)):
         # Cholesky does half of it, so "tflops" below is an equivalent rate, comparable across solvers
         flops = 2.0 / 3.0 * N ** 3 + 2.0 * N ** 2 + 0.5 * n * n * (3 * 10 + 4)
         resid = float(np.max(np.abs(s.predict(X[:2000]) + s.eta * s.c[11:11 + min(n, 2000)] - fX[:2000])))
-        out.append({"n": n, "d": 10, "kernel": "tps", "solver": s.handle.last_fit_method, "seconds_device": best_dev,
-                    "seconds_host_to_host": best_wall,
-                    "tflops": flops / best_dev / 1e12, "interp_residual": resid})
+        rec = {"n": n, "d": 10, "kernel": "tps", "solver": s.handle.last_fit_method, "seconds_device": best_dev,
+               "seconds_host_to_host": best_wall, "tflops": flops / best_dev / 1e12, "interp_residual": resid}
+        if n == sizes[-1]:
+            # config #3's other half: predict on 1e5 points (seed 1), and predict_deriv, host arrays in and out
+            q = np.random.default_rng(1).random((100000, 10))
+            s.predict(q[:1000])
+            t0 = time.perf_counter()
+            s.predict(q)
+            rec["predict_pairs_per_s"] = q.shape[0] * n / (time.perf_counter() - t0)
+            s.predict_deriv(q[:100])
+            t0 = time.perf_counter()
+            s.predict_deriv(q[:5000])
+            rec["predict_deriv_pairs_per_s"] = 5000 * n / (time.perf_counter() - t0)
+        out.append(rec)
         del s
     return out
 

@@ -5,13 +5,14 @@
 // s_j = phi'(r_j) c_j / r_j; phase 2 (thread per coordinate x center slice) accumulates (u_k - u_jk) s_j in
 // the reference's operation order; a second tiny kernel adds the slab partials in slab order, the tail
 // derivative (tails/linear_tail.py:46, constant_tail.py:44) and divides by the box width (rbf.py:215).
-#include "common.cuh"
+#include "deriv_tile.cuh"
 
 namespace b200rbf {
 namespace {
 
 constexpr int kDerivThreads = 256;
 constexpr int kSlab = 512;
+constexpr long long kDerivTileMinQueries = 4096;  // below this a thread per query cannot fill 148 SMs
 
 __device__ __forceinline__ double dphi_times_c_over_r(int kern, double r, double c) {
   // kernels/cubic_kernel.py:37 3 r^2 ; tps_kernel.py:41-42 r (1 + 2 log r) ; linear_kernel.py:40 1
@@ -99,6 +100,20 @@ __global__ void deriv_final_kernel(const double* __restrict__ partial, int nslab
 int launch_deriv(b200rbf_ctx* h, const double* x, long long m, const double* lb, const double* range, double* out,
                  double* scratch) {
   const Model& M = h->model;
+  if (m >= kDerivTileMinQueries && M.dpad <= kMaxRegDim) {
+    // enough queries to fill the GPU with one thread each: the tile-streaming kernel (deriv_tile.cuh)
+    DerivTileArgs a;
+    a.x = x; a.m = m; a.d = M.d; a.lb = lb; a.range = range;
+    a.pts = M.centers_x.as<double>(); a.coef = M.coef.as<double>(); a.tailc = M.tailc.as<double>();
+    a.ds = M.ds; a.npad = M.npad; a.tail = M.tail; a.out = out;
+    const int k4 = (M.d + 3) / 4;
+    switch ((k4 - 1) / 4) {
+      case 0: return launch_deriv_tile_group0(h, a, k4, M.kernel);
+      case 1: return launch_deriv_tile_group1(h, a, k4, M.kernel);
+      case 2: return launch_deriv_tile_group2(h, a, k4, M.kernel);
+      default: return launch_deriv_tile_group3(h, a, k4, M.kernel);
+    }
+  }
   const int nslabs = (M.n + kSlab - 1) / kSlab;
   const size_t smem = ((size_t)M.d + kSlab + kDerivThreads) * sizeof(double);
   auto kern = h->exact_dist ? deriv_partial_kernel<true> : deriv_partial_kernel<false>;
@@ -124,7 +139,8 @@ int launch_deriv(b200rbf_ctx* h, const double* x, long long m, const double* lb,
 int deriv_scratch_doubles(const b200rbf_ctx* h, long long m, size_t* out) {
   const Model& M = h->model;
   const int nslabs = (M.n + kSlab - 1) / kSlab;
-  *out = (size_t)m * nslabs * M.d;
+  const bool tile = m >= kDerivTileMinQueries && M.dpad <= kMaxRegDim;  // the tile kernel needs no partials
+  *out = tile ? 0 : (size_t)m * nslabs * M.d;
   return 0;
 }
 

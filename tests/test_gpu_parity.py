@@ -502,3 +502,28 @@ def test_lu_lookahead_and_gemm_variants_give_identical_coefficients(pb):
             assert np.array_equal(s.c, ref), (look, variant)  # same products, same order within each accumulator
         else:
             assert relmax(s.c, ref) < 1e-7  # different algorithm: coefficients agree to cond * eps
+
+
+@pytest.mark.parametrize("kernel,tail,d", [("cubic", "linear", 10), ("tps", "linear", 50), ("linear", "constant", 3),
+                                           ("linear", "linear", 7), ("cubic", "linear", 64)])
+def test_predict_deriv_many_queries_uses_the_tile_kernel(pb, orc, kernel, tail, d):
+    """>= 4096 query points take the tile-streaming gradient kernel (deriv_tile.cuh); fewer take the slab kernel.
+    Both against the oracle's Python loop (rbf.py:204-214), including queries that coincide with centers."""
+    rng = np.random.default_rng(d)
+    n = 2 * d + 150
+    lb, ub = rng.uniform(-3, 0, d), rng.uniform(1, 4, d)
+    X = lb + (ub - lb) * rng.random((n, d))
+    fX = np.sin(((X - lb) / (ub - lb)).sum(1))[:, None]
+    s = make_gpu(pb, d, lb, ub, kernel, tail)
+    s.add_points(X, fX)
+    o = orc.OracleRBF(d, lb, ub, kernel, tail)
+    o.add_points(X, fX)
+    q = lb + (ub - lb) * rng.random((4500, d))
+    q[:20] = X[:20]
+    big = s.predict_deriv(q)
+    small = s.predict_deriv(q[:300])
+    ref = o.predict_deriv(q[:300])
+    assert big.shape == (4500, d)
+    assert relmax(small, ref) < TOL and relmax(big[:300], ref) < TOL
+    ref_tail = o.predict_deriv(q[-50:])
+    assert relmax(big[-50:], ref_tail) < TOL
