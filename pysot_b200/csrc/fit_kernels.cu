@@ -482,17 +482,19 @@ __global__ void __launch_bounds__(kBsBlock) diag_upper_solve_kernel(const double
   extern __shared__ double su[];  // rows x (kBsBlock + 1)
   __shared__ double sx[kBsBlock];
   const int st = kBsBlock + 1, tid = threadIdx.x;
-  for (int e = tid; e < rows * rows; e += blockDim.x) {
-    const int i = e / rows, k = e - i * rows;
-    su[i * st + k] = A[(size_t)(r0 + i) * ld + r0 + k];
-  }
+  for (int i = 0; i < rows; ++i)  // thread = column: coalesced row reads, no integer division
+    if (tid < rows) su[i * st + tid] = A[(size_t)(r0 + i) * ld + r0 + tid];
   double v = (tid < rows) ? y[r0 + tid] : 0.0;
   __syncthreads();
+  double rdiag = 0.0;  // reciprocals of the diagonal, all at once and off the critical path (as LAPACK's dtrsv does not,
+  if (tid < rows) {    // but dgetf2 does for its pivots)
+    const double dgl = su[tid * st + tid];
+    if (dgl == 0.0) atomicCAS(info, 0, r0 + tid + 1);
+    rdiag = 1.0 / dgl;
+  }
   for (int k = rows - 1; k >= 0; --k) {
     if (tid == k) {
-      const double dgl = su[k * st + k];
-      if (dgl == 0.0 && *info == 0) *info = r0 + k + 1;
-      v = v / dgl;
+      v *= rdiag;
       sx[k] = v;
     }
     __syncthreads();

@@ -192,9 +192,11 @@ __global__ void __launch_bounds__(kUpdRows) update_kernel(const double* __restri
     const long long total = rows * d;
     const double* src = cand + base * d;
     __syncthreads();
-    for (long long e = tid; e < total; e += blockDim.x) {
-      const int r = (int)(e / d), k = (int)(e - (long long)r * d);
-      s_rows[r * ds + k] = src[e];
+    // warp w stages rows w, w + nwarps, ...; lanes run over the coordinates: coalesced, no integer division
+    (void)total;
+    for (int r = tid >> 5; r < (int)rows; r += blockDim.x >> 5) {
+      const double* rp = src + (long long)r * d;
+      for (int k = tid & 31; k < d; k += 32) s_rows[r * ds + k] = rp[k];
     }
     __syncthreads();
     if (tid < rows) {
