@@ -37,6 +37,9 @@ constexpr int kMmaJB = B2_MMA_JB;          // n8 center blocks per step (8 * JB 
 constexpr int kMmaMinBlocks = B2_MMA_MINB; // CTAs per SM the register budget is capped for (+1 when d <= 16);
                                            // tools/k2x_tune.cu sweep: 2 x 4 beats 2 x 3 by 6 %, 4 x 2 by 16 % at d = 50
 constexpr int kMmaTileRows = 8 * kMmaJB;   // center rows per tile
+#ifndef B2_MMA_EMPTY_BAR
+#define B2_MMA_EMPTY_BAR 0
+#endif
 #ifndef B2_MMA_STAGES
 #define B2_MMA_STAGES 3
 #endif
@@ -77,7 +80,8 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 <= 4 ? kMmaMinBlocks + 1 : kM
   double* s_wts = s_pts + (size_t)kMmaStages * kMmaTileRows * ds;          // [stages][rows]
   double* s_nrm = s_wts + kMmaStages * kMmaTileRows;                       // [stages][rows]
   uint64_t* s_full = reinterpret_cast<uint64_t*>(s_nrm + kMmaStages * kMmaTileRows);
-  double* s_red = reinterpret_cast<double*>(s_full + kMmaStages);         // 4 x warps
+  uint64_t* s_empty = s_full + kMmaStages;                               // consumer release, one arrival per warp
+  double* s_red = reinterpret_cast<double*>(s_empty + kMmaStages);        // 4 x warps
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gid = lane >> 2, tig = lane & 3;
@@ -85,7 +89,10 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 <= 4 ? kMmaMinBlocks + 1 : kM
   const int ntiles = (a.npad + kMmaTileRows - 1) / kMmaTileRows;
 
   if (tid == 0) {
-    for (int s = 0; s < kMmaStages; ++s) mbar_init(&s_full[s], 1);
+    for (int s = 0; s < kMmaStages; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], kMmaThreads / 32);
+    }
     fence_barrier_init();
   }
   __syncthreads();
@@ -184,8 +191,19 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 <= 4 ? kMmaMinBlocks + 1 : kM
         }
       }
     }
+#if B2_MMA_EMPTY_BAR
+    // no CTA-wide barrier in the main loop: each warp releases the stage, the producer thread waits for all four
+    // releases before refilling it, the other warps run ahead by up to the ring depth
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s_empty[s]);
+    if (tid == 0 && t + kMmaStages < ntiles) {
+      mbar_wait(&s_empty[s], (uint32_t)((t / kMmaStages) & 1));
+      issue(t + kMmaStages);
+    }
+#else
     __syncthreads();
     if (tid == 0 && t + kMmaStages < ntiles) issue(t + kMmaStages);
+#endif
   }
 
   // combine the quad's partial results (fixed order: deterministic)
@@ -260,7 +278,7 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 <= 4 ? kMmaMinBlocks + 1 : kM
 }
 
 inline size_t score_mma_smem_bytes(int ds) {
-  return ((size_t)kMmaStages * kMmaTileRows * ds + 2 * (size_t)kMmaStages * kMmaTileRows + kMmaStages +
+  return ((size_t)kMmaStages * kMmaTileRows * ds + 2 * (size_t)kMmaStages * kMmaTileRows + 2 * kMmaStages +
           4 * (kMmaThreads / 32)) * 8;
 }
 

@@ -173,3 +173,15 @@ def test_install_rebinds_reference_names():
     finally:
         cnd.uninstall()
     assert ds.candidate_dycors is orig
+
+
+def test_candidate_generator_switch():
+    assert cnd._GENERATOR["mode"] == "host"
+    with pytest.raises(ValueError):
+        pb.set_candidate_generator("gpu")
+    pb.set_candidate_generator("device", seed=5)
+    try:
+        assert cnd._GENERATOR == {"mode": "device", "seed": 5, "calls": 0}
+    finally:
+        pb.set_candidate_generator("host")
+    assert cnd._GENERATOR["mode"] == "host"

@@ -57,6 +57,7 @@ class Recorder:
     def __init__(self, kind, ref_fn, want_deriv=False):
         self.kind, self.ref_fn, self.want_deriv = kind, ref_fn, want_deriv
         self.calls, self.states, self.last_post = [], [], None
+        self.ref_seconds = []  # wall time of each unmodified reference call (fit + generation + merit)
         self.strategy = None
         # every row that ever was in the strategy's current-run arrays (_X, _fX), in order; a call refers to the
         # contiguous slice [start, start + n).  (_X is NOT a slice of X: evaluations proposed before a radius
@@ -65,7 +66,9 @@ class Recorder:
 
     def __call__(self, **kw):
         pre = np.random.get_state()
-        pts = self.ref_fn(**kw)
+        t0 = time.perf_counter()
+        pts = self.ref_fn(**kw)  # includes the lazy (incremental) refit inside surrogate.predict
+        self.ref_seconds.append(time.perf_counter() - t0)
         post = np.random.get_state()
         # oracle replay from the same state: candidate set, picks and merit margins
         np.random.set_state(pre)
@@ -130,7 +133,7 @@ class Recorder:
             picked=np.concatenate([r["picked"] for r in c]),
             state_call=np.array([s[0] for s in self.states]), state_key=np.vstack([s[1][1] for s in self.states]),
             state_pos=np.array([s[1][2] for s in self.states]), state_gauss=np.array([s[1][3] for s in self.states]),
-            state_cached=np.array([s[1][4] for s in self.states]), **extra)
+            state_cached=np.array([s[1][4] for s in self.states]), ref_call_seconds=np.array(self.ref_seconds), **extra)
         if self.want_deriv:
             for key in ("deriv", "pred", "deriv_full", "pred_full"):
                 out[key] = np.vstack([r[key] for r in c])
