@@ -1,6 +1,7 @@
 """Teacher-forced replay of the strategy traces written by tools/make_strategy_traces.py (shared by the CPU oracle
 test and the GPU parity test)."""
 import os
+import time
 
 import numpy as np
 import pytest
@@ -30,11 +31,14 @@ class OracleBackend:
         return self.orc.OracleRBF(d, lb, ub, "cubic", "linear")
 
 
-def replay(fname, backend, max_calls=None):
+def replay(fname, backend, max_calls=None, timer=None):
+    """timer: optional dict; timer["seconds"] accumulates the wall-clock of add_points + the candidate_* call (what the
+    trace's ref_call_seconds holds for the reference: its lazy refit happens inside the call)."""
     path = os.path.join(GOLDEN, fname)
     if not os.path.exists(path):
         pytest.skip("%s not generated" % fname)
-    g = np.load(path)
+    with np.load(path) as z:
+        g = {k: z[k] for k in z.files}  # NpzFile re-reads the archive member on every access
     d = int(g["dim"])
     prob = Problem(g["lb"], g["ub"], g["int_var"])
     kind = str(g["kind"])
@@ -50,6 +54,7 @@ def replay(fname, backend, max_calls=None):
             s.reset()
             seg, have = int(g["seg"][i]), 0
         n = int(g["n"][i])
+        t_start = time.perf_counter()
         if n > have:
             s.add_points(g["allX"][seg + have:seg + n], g["allfX"][seg + have:seg + n])
             have = n
@@ -70,6 +75,8 @@ def replay(fname, backend, max_calls=None):
         else:
             pts = backend.candidate_srbf(num_pts=p, opt_prob=prob, surrogate=s, X=X, fX=fX, weights=w, Xpend=Xpend,
                                     sampling_radius=float(g["sampling_radius"][i]), num_cand=int(g["num_cand"][i]))
+        if timer is not None:
+            timer["seconds"] = timer.get("seconds", 0.0) + time.perf_counter() - t_start
         ref = g["new_points"][pt_off[i]:pt_off[i + 1]]
         if not np.array_equal(pts, ref):
             first = int(np.argmax(np.any(pts != ref, axis=1)))
@@ -77,7 +84,7 @@ def replay(fname, backend, max_calls=None):
                 ties += 1
             else:
                 mismatches.append((i, first, float(g["margins"][pt_off[i] + first])))
-        if "deriv" in g.files:  # config #5 add-on: value and gradient at every proposed point
+        if "deriv" in g:  # config #5 add-on: value and gradient at every proposed point
             sl = slice(pt_off[i], pt_off[i + 1])
             gd, gp = s.predict_deriv(ref), s.predict(ref)
             for key in ("deriv", "deriv_full"):

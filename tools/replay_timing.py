@@ -7,7 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import pysot_b200 as pb
-from trace_replay import GpuBackend, replay
+from trace_replay import GpuBackend, OracleBackend, replay
 from conftest import GOLDEN
 
 out = []
@@ -20,11 +20,15 @@ for name, label in (("trace_dycors.npz", "#1 DYCORS Ackley-10 serial, 500 evals"
     for mode in ("host", "device"):
         pb.set_candidate_generator(mode, seed=1)
         replay(name, GpuBackend(), max_calls=20)  # warm-up (library load, buffers)
-        t0 = time.perf_counter()
-        ncalls, mism, ties, err = replay(name, GpuBackend())
-        row["gpu_seconds_%s_candidates" % mode] = time.perf_counter() - t0
+        tm = {}
+        ncalls, mism, ties, err = replay(name, GpuBackend(), timer=tm)
+        row["gpu_seconds_%s_candidates" % mode] = tm["seconds"]
         if mode == "host":
             row["mismatches"] = len(mism)
     pb.set_candidate_generator("host")
+    if "--no-oracle" not in sys.argv:  # the oracle (bit-identical to the reference, incremental LU included) on THIS host
+        tm = {}
+        replay(name, OracleBackend(), timer=tm)
+        row["oracle_cpu_seconds_this_host"] = tm["seconds"]
     out.append(row)
     print(json.dumps(row), flush=True)
