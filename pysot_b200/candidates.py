@@ -128,15 +128,91 @@ def _scale_factors(opt_prob, sampling_radius, subset):
     return sf
 
 
+# scipy draws a truncated normal by inversion: U = random_state.uniform(size), x = truncnorm._ppf(U, a, b), then
+# x * scale + loc (rv_generic.rvs / rv_generic._rvs).  The reference calls it once per coordinate with scalar a, b, and
+# _ppf re-evaluates the two quantities that depend on (a, b) only -- log Phi(a) and the log mass of [a, b] -- for every
+# sample.  _truncnorm_rvs_batch makes the same draws for all coordinates in one pass with those two hoisted; every
+# remaining operation is the element-wise one _ppf applies, so the variates (and the state of numpy's global stream)
+# are bit-identical.  It leans on scipy internals, so the first use checks it against the public truncnorm.rvs and any
+# difference (or a scipy without those internals) switches it off for the process.
+_FAST_TRUNCNORM = {"ok": None}
+
+
+def _truncnorm_from_uniform(q, a, b, loc, scale, counts):
+    from scipy import special as sc
+    from scipy.stats import _continuous_distns as cd
+
+    left = a < 0
+    lcdf = np.where(left, cd._norm_logcdf(np.where(left, a, 0.0)), cd._norm_logcdf(np.where(left, 0.0, -b)))
+    lmass = cd._log_gauss_mass(a, b)
+    rep_left = np.repeat(left, counts)
+    with np.errstate(divide="ignore"):
+        logq = np.log(q) if left.all() else np.where(rep_left, np.log(q), np.log1p(-q))
+    x = sc.ndtri_exp(_log_sum_pairs(np.repeat(lcdf, counts), logq + np.repeat(lmass, counts), cd._log_sum))
+    if not left.all():
+        x = np.where(rep_left, x, -x)
+    x *= np.repeat(scale, counts)
+    x += np.repeat(loc, counts)
+    return x
+
+
+def _log_sum_pairs(p, q, scipy_log_sum):
+    """log(exp(p) + exp(q)) with the arithmetic of scipy.special.logsumexp([p, q], axis=0) -- which is what
+    truncnorm._ppf calls -- for the generic element: the maximum is split off, the other term enters as
+    log1p(exp(lo - hi)), then + log(1) + hi.  Ties and non-finite elements take scipy's own routine."""
+    hi, lo = np.maximum(p, q), np.minimum(p, q)
+    with np.errstate(all="ignore"):
+        lo -= hi
+        out = np.log1p(np.exp(lo, out=lo), out=lo)
+        out += 0.0
+        out += hi
+    # lo - hi == 0 is a tie; a non-finite p, q or result shows up as a non-finite `out` or hi
+    odd = ~np.isfinite(out) | (p == q)
+    if odd.any():
+        out[odd] = scipy_log_sum(p[odd], q[odd])
+    return out
+
+
+def _fast_truncnorm_ok():
+    if _FAST_TRUNCNORM["ok"] is None:
+        try:
+            a = np.array([-1.3, 0.2, -7.5, 3.0, -0.0, 1e-3, -40.0, 0.0, -175.0, 12.0, -1e-9, -3.5])
+            b = np.array([2.1, 0.9, -6.0, 9.0, 4.0, 8.0, 40.0, 1e-6, 0.0, 175.0, 1e-9, 5.0])
+            loc = np.array([0.4, -3.0, 10.0, 0.0, 1.0, -1.0, 0.0, 2.0, 20.0, -15.0, 0.5, 0.0])
+            scale = np.array([0.2, 7.0, 1.0, 0.05, 3.0, 1.0, 0.5, 7.0, 0.2, 0.2, 1e3, 1.0])
+            counts = np.array([370, 5, 640, 0, 190, 80, 300, 100, 200, 200, 100, 1000])
+            rs = np.random.RandomState(12345)
+            want = np.concatenate([stats.truncnorm.rvs(a=a[i], b=b[i], loc=loc[i], scale=scale[i], size=int(counts[i]),
+                                                       random_state=rs) for i in range(len(a))])
+            got = _truncnorm_from_uniform(np.random.RandomState(12345).uniform(size=int(counts.sum())), a, b, loc,
+                                          scale, counts)
+            _FAST_TRUNCNORM["ok"] = bool(np.array_equal(want, got))
+        except Exception:  # scipy without these internals
+            _FAST_TRUNCNORM["ok"] = False
+    return _FAST_TRUNCNORM["ok"]
+
+
+def _truncnorm_rvs_batch(a, b, loc, scale, counts):
+    """Concatenation of ``truncnorm.rvs(a[i], b[i], loc[i], scale[i], size=counts[i])`` for i = 0, 1, ... drawn from
+    numpy's global stream in that order."""
+    a, b, loc, scale = (np.asarray(v, dtype=np.float64) for v in (a, b, loc, scale))
+    counts = np.asarray(counts, dtype=np.int64)
+    if not _fast_truncnorm_ok() or not (np.all(a < b) and np.all(scale > 0)):  # odd arguments: scipy's own checks
+        return np.concatenate([stats.truncnorm.rvs(a=a[i], b=b[i], loc=loc[i], scale=scale[i], size=int(counts[i]))
+                               for i in range(len(a))] + [np.empty(0)])
+    return _truncnorm_from_uniform(np.random.uniform(size=int(counts.sum())), a, b, loc, scale, counts)
+
+
 def generate_srbf(opt_prob, X, fX, sampling_radius=0.2, subset=None, num_cand=None):
     """Truncated-normal perturbation of every coordinate in ``subset`` around xbest (candidate_srbf.py:91-116)."""
     xbest, num_cand, subset = _prepare(opt_prob, X, fX, subset, num_cand)
     sf = _scale_factors(opt_prob, sampling_radius, subset)
     cand = np.multiply(np.ones((num_cand, opt_prob.dim)), xbest)
-    for i in subset:
-        lo, hi, s = opt_prob.lb[i], opt_prob.ub[i], sf[i]
-        cand[:, i] = stats.truncnorm.rvs(a=(lo - xbest[i]) / s, b=(hi - xbest[i]) / s, loc=xbest[i], scale=s,
-                                         size=num_cand)
+    sub = np.asarray(subset, dtype=np.int64)
+    if len(sub) > 0:
+        lo, hi, s, xb = opt_prob.lb[sub], opt_prob.ub[sub], sf[sub], xbest[sub]
+        draws = _truncnorm_rvs_batch((lo - xb) / s, (hi - xb) / s, xb, s, np.full(len(sub), num_cand))
+        cand[:, sub] = draws.reshape(len(sub), num_cand).T  # a repeated coordinate keeps its last draw, as in the loop
     return _round_vars(cand, opt_prob.int_var, opt_prob.lb, opt_prob.ub)
 
 
@@ -154,11 +230,17 @@ def generate_dycors(opt_prob, X, fX, prob_perturb, sampling_radius=0.2, subset=N
         ind = np.where(np.sum(ar, axis=1) == 0)[0]
         ar[ind, np.random.randint(0, len(subset) - 1, size=len(ind))] = 1
     cand = np.multiply(np.ones((num_cand, opt_prob.dim)), xbest)
-    for i in subset:
-        lo, hi, s = opt_prob.lb[i], opt_prob.ub[i], sf[i]
-        ind = np.where(ar[:, i] == 1)[0]
-        cand[ind, subset[i]] = stats.truncnorm.rvs(a=(lo - xbest[i]) / s, b=(hi - xbest[i]) / s, loc=xbest[i],
-                                                   scale=s, size=len(ind))
+    sub = np.asarray(subset, dtype=np.int64)
+    if len(sub) > 0:
+        # the reference's loop `for i in subset` indexes the mask column, the bounds and xbest with i and writes
+        # column subset[i] (candidate_dycors.py:83-89); kept as is
+        lo, hi, s, xb = opt_prob.lb[sub], opt_prob.ub[sub], sf[sub], xbest[sub]
+        rows = [np.where(ar[:, i] == 1)[0] for i in sub]
+        draws = _truncnorm_rvs_batch((lo - xb) / s, (hi - xb) / s, xb, s, [len(r) for r in rows])
+        off = 0
+        for i, ind in zip(sub, rows):
+            cand[ind, subset[i]] = draws[off:off + len(ind)]
+            off += len(ind)
     return _round_vars(cand, opt_prob.int_var, opt_prob.lb, opt_prob.ub)
 
 

@@ -185,3 +185,12 @@ def test_candidate_generator_switch():
     finally:
         pb.set_candidate_generator("host")
     assert cnd._GENERATOR["mode"] == "host"
+
+
+def test_batched_truncnorm_is_bit_identical_to_scipy_loop():
+    """The host generators draw all coordinates in one pass (candidates._truncnorm_rvs_batch); candidate sets and the
+    state of numpy's global stream must equal the reference's per-coordinate truncnorm.rvs loop bit for bit."""
+    from tools import check_host_generators as chk
+
+    assert cnd._fast_truncnorm_ok()
+    assert chk.run(cases=80, seed=5) == 0
