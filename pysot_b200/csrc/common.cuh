@@ -117,7 +117,7 @@ constexpr int kJT = B2_JT;                      // centers processed together pe
 constexpr int kGenMaxDim = 192;                 // largest padded dimension of the shared-memory (generic) score kernel
 
 inline int pad_dim(int d) { return (d + 1) & ~1; }                       // even: rows are multiples of 16 B
-inline int pad_rows(int n) { return (n + 15) & ~15; }                    // multiples of 16 (duplicates of last row)
+inline int pad_rows(int n) { return (n + 31) & ~31; }                    // multiples of 32 (duplicates of last row)
 inline int mma_stride(int d) {                                            // center row stride of the DMMA kernel:
   int s = (d + 3) & ~3;                                                   // >= 4 ceil(d/4), == 4 (mod 16) doubles so the
   while ((s & 15) != 4) s += 4;                                           // B-fragment LDS.64 are bank-conflict free

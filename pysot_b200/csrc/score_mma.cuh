@@ -37,6 +37,7 @@ constexpr int kMmaJB = B2_MMA_JB;          // n8 center blocks per step (8 * JB 
 constexpr int kMmaMinBlocks = B2_MMA_MINB; // CTAs per SM the register budget is capped for (+1 when d <= 16);
                                            // tools/k2x_tune.cu sweep: 2 x 4 beats 2 x 3 by 6 %, 4 x 2 by 16 % at d = 50
 constexpr int kMmaTileRows = 8 * kMmaJB;   // center rows per tile
+static_assert(32 % kMmaTileRows == 0, "pad_rows() pads the center rows to multiples of 32: tiles must divide that");
 #ifndef B2_MMA_EMPTY_BAR
 #define B2_MMA_EMPTY_BAR 0
 #endif
@@ -56,6 +57,33 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
                : "+d"(d0), "+d"(d1)
                : "d"(a), "d"(b));
+}
+
+#ifndef B2_MMA_FAST_SQRT
+#define B2_MMA_FAST_SQRT 2
+#endif
+// phi(r) from r^2 in the DMMA kernel.  The cubic / linear kernels take the square root as B2_MMA_FAST_SQRT corrections
+// s <- s + (x - s^2) y / 2 of the hardware reciprocal-square-root seed y (MUFU.RSQ64H, measured 2^-20), starting from
+// s = x y.  Measured against sqrt() (tools/sqrt_probe.cu): one correction 1.3e-12, two corrections 2.2e-16 relative
+// (within one ulp) -- five FP64 operations, and, unlike sqrt(), no slow-path call, so the 16 chains of a thread sit in
+// one basic block and interleave.  0 selects sqrt().
+template <int KERN>
+__device__ __forceinline__ double mma_phi_from_r2(double r2) {
+#if B2_MMA_FAST_SQRT
+  if (KERN != B200RBF_KERNEL_TPS) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(r2));
+    const double g = r2 * y;
+    const double h = __longlong_as_double(__double_as_longlong(y) - (1LL << 52));  // y / 2 on the integer pipe
+    double s = fma(fma(-g, g, r2), h, g);
+#if B2_MMA_FAST_SQRT >= 2
+    s = fma(fma(-s, s, r2), h, s);  // second correction: ~1 ulp
+#endif
+    if (__double_as_longlong(r2) < (1LL << 52)) s = 0.0;  // zero / subnormal r^2: the seed is +inf
+    return KERN == B200RBF_KERNEL_CUBIC ? r2 * s : s;
+  }
+#endif
+  return rbf_phi_from_r2<KERN>(r2);
 }
 
 // direct squared distance of candidate `row` to the shared-memory center row `cp` (slow path for near pairs)
@@ -146,12 +174,12 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 <= 4 ? kMmaMinBlocks + 1 : kM
 
   for (int t = 0; t < ntiles; ++t) {
     const int s = t % kMmaStages;
-    const int rows = min(kMmaTileRows, a.npad - t * kMmaTileRows);  // multiple of 16
+    const int rows = min(kMmaTileRows, a.npad - t * kMmaTileRows);  // always a full tile (see pad_rows)
     mbar_wait(&s_full[s], (uint32_t)((t / kMmaStages) & 1));
     const double* tp = s_pts + (size_t)s * kMmaTileRows * ds;
     const double* tw = s_wts + s * kMmaTileRows;
     const double* tn = s_nrm + s * kMmaTileRows;
-    for (int j0 = 0; j0 < rows; j0 += 8 * kMmaJB) {  // npad is a multiple of 16; a short last step repeats valid rows
+    for (int j0 = 0; j0 < rows; j0 += 8 * kMmaJB) {  // npad is a multiple of 32 = 8 kMmaJB: tiles are always full
       double acc[kMmaMB][kMmaJB][2];
 #pragma unroll
       for (int i = 0; i < kMmaMB; ++i)
@@ -168,25 +196,54 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 <= 4 ? kMmaMinBlocks + 1 : kM
 #pragma unroll
           for (int jb = 0; jb < kMmaJB; ++jb) dmma884(acc[i][jb][0], acc[i][jb][1], afr[i][k], bfr[jb]);
       }
+      // Epilogue in three passes so that the common case is branch-free and the 16 sqrt chains of a thread can be
+      // interleaved by the scheduler (a call inside the per-pair sequence serialises them):
+      // (1) r^2 = |u|^2 + |c|^2 - 2 u.c in place of the dot products, near flags OR-ed together.
+      // The near test r2 < 2^-10 sq runs on the INTEGER pipe (the FP64 pipe is the bottleneck): for non-negative
+      // doubles the bit patterns order like the values, 2^-10 sq is sq with its exponent lowered by 10, and a
+      // negative r2 (cancellation) is a negative integer, i.e. below any threshold.
+      bool near_any = false;
 #pragma unroll
       for (int jb = 0; jb < kMmaJB; ++jb) {
-        if (j0 + 8 * jb >= rows) break;  // tile shorter than a full step (npad % 32 == 16)
-        const int jc = j0 + 8 * jb + 2 * tig;
-        const double2 n2 = *reinterpret_cast<const double2*>(tn + jc);
-        const double2 w2 = *reinterpret_cast<const double2*>(tw + jc);
+        const double2 n2 = *reinterpret_cast<const double2*>(tn + j0 + 8 * jb + 2 * tig);
 #pragma unroll
         for (int i = 0; i < kMmaMB; ++i) {
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const double sq = nx[i] + (e ? n2.y : n2.x);
-            double r2 = fma(-2.0, acc[i][jb][e], sq);
-            // near test r2 < 2^-10 sq and the running minimum on the INTEGER pipe (the FP64 pipe is the bottleneck):
-            // for non-negative doubles the bit patterns order like the values, 2^-10 sq is sq with its exponent
-            // lowered by 10, and a negative r2 (cancellation) is a negative integer, i.e. below any threshold
-            if (__double_as_longlong(r2) < __double_as_longlong(sq) - kNearShift)
-              r2 = mma_exact_r2(a.cand + rows_i[i] * (long long)a.d, a.d, a.lb, a.range, tp + (jc + e) * ds);
-            mnb[i] = min(mnb[i], __double_as_longlong(r2));  // r2 >= 0 here
-            sum[i] = fma(rbf_phi_from_r2<KERN>(r2), e ? w2.y : w2.x, sum[i]);
+            const double r2 = fma(-2.0, acc[i][jb][e], sq);
+            near_any |= __double_as_longlong(r2) < __double_as_longlong(sq) - kNearShift;
+            acc[i][jb][e] = r2;
+          }
+        }
+      }
+      // (2) rare: recompute the near pairs directly (same arithmetic as score_kernel, so they are bit-identical to it)
+      if (near_any) {
+#pragma unroll
+        for (int jb = 0; jb < kMmaJB; ++jb) {
+          const int jc = j0 + 8 * jb + 2 * tig;
+#pragma unroll
+          for (int i = 0; i < kMmaMB; ++i) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const double sq = nx[i] + tn[jc + e];
+              if (__double_as_longlong(acc[i][jb][e]) < __double_as_longlong(sq) - kNearShift)
+                acc[i][jb][e] = mma_exact_r2(a.cand + rows_i[i] * (long long)a.d, a.d, a.lb, a.range, tp + (jc + e) * ds);
+            }
+          }
+        }
+      }
+      // (3) running minimum (integer pipe, r2 >= 0 here) and the weighted kernel sum, same summation order as before
+#pragma unroll
+      for (int jb = 0; jb < kMmaJB; ++jb) {
+        const double2 w2 = *reinterpret_cast<const double2*>(tw + j0 + 8 * jb + 2 * tig);
+#pragma unroll
+        for (int i = 0; i < kMmaMB; ++i) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const double r2 = acc[i][jb][e];
+            mnb[i] = min(mnb[i], __double_as_longlong(r2));
+            sum[i] = fma(mma_phi_from_r2<KERN>(r2), e ? w2.y : w2.x, sum[i]);
           }
         }
       }
