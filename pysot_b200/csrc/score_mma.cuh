@@ -71,15 +71,17 @@ template <int KERN>
 __device__ __forceinline__ double mma_phi_from_r2(double r2) {
 #if B2_MMA_FAST_SQRT
   if (KERN != B200RBF_KERNEL_TPS) {
+    // the seed reads only the high word; clamping it to the smallest normal keeps the seed finite for r2 = 0 (then
+    // g = s = 0 exactly) and for subnormal r2 (sqrt < 1e-154: its error is invisible) without any select afterwards
+    const int hi = max(__double2hiint(r2), 0x00100000);
     double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(r2));
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(__hiloint2double(hi, 0)));
     const double g = r2 * y;
-    const double h = __longlong_as_double(__double_as_longlong(y) - (1LL << 52));  // y / 2 on the integer pipe
+    const double h = __hiloint2double(__double2hiint(y) - 0x00100000, 0);  // y / 2 on the integer pipe (low word is 0)
     double s = fma(fma(-g, g, r2), h, g);
 #if B2_MMA_FAST_SQRT >= 2
     s = fma(fma(-s, s, r2), h, s);  // second correction: ~1 ulp
 #endif
-    if (__double_as_longlong(r2) < (1LL << 52)) s = 0.0;  // zero / subnormal r^2: the seed is +inf
     return KERN == B200RBF_KERNEL_CUBIC ? r2 * s : s;
   }
 #endif
@@ -170,7 +172,7 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 <= 4 ? kMmaMinBlocks + 1 : kM
     sum[i] = 0.0;
     mnb[i] = 0x7ff0000000000000LL;
   }
-  constexpr long long kNearShift = 10LL << 52;  // near pairs: r^2 < 2^-10 (|u|^2 + |c|^2)
+  constexpr int kNearShiftHi = 10 << 20;  // near pairs: r^2 < 2^-10 (|u|^2 + |c|^2), tested on the high words
 
   for (int t = 0; t < ntiles; ++t) {
     const int s = t % kMmaStages;
@@ -199,9 +201,9 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 <= 4 ? kMmaMinBlocks + 1 : kM
       // Epilogue in three passes so that the common case is branch-free and the 16 sqrt chains of a thread can be
       // interleaved by the scheduler (a call inside the per-pair sequence serialises them):
       // (1) r^2 = |u|^2 + |c|^2 - 2 u.c in place of the dot products, near flags OR-ed together.
-      // The near test r2 < 2^-10 sq runs on the INTEGER pipe (the FP64 pipe is the bottleneck): for non-negative
-      // doubles the bit patterns order like the values, 2^-10 sq is sq with its exponent lowered by 10, and a
-      // negative r2 (cancellation) is a negative integer, i.e. below any threshold.
+      // The near test r2 < 2^-10 sq runs on the INTEGER pipe (the FP64 pipe is the bottleneck) and on the high words
+      // only: for non-negative doubles the bit patterns order like the values, 2^-10 sq is sq with its exponent
+      // lowered by 10, and a negative r2 (cancellation) is a negative integer, i.e. below any threshold.
       bool near_any = false;
 #pragma unroll
       for (int jb = 0; jb < kMmaJB; ++jb) {
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 <= 4 ? kMmaMinBlocks + 1 : kM
           for (int e = 0; e < 2; ++e) {
             const double sq = nx[i] + (e ? n2.y : n2.x);
             const double r2 = fma(-2.0, acc[i][jb][e], sq);
-            near_any |= __double_as_longlong(r2) < __double_as_longlong(sq) - kNearShift;
+            near_any |= __double2hiint(r2) < __double2hiint(sq) - kNearShiftHi;
             acc[i][jb][e] = r2;
           }
         }
@@ -227,13 +229,18 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 <= 4 ? kMmaMinBlocks + 1 : kM
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               const double sq = nx[i] + tn[jc + e];
-              if (__double_as_longlong(acc[i][jb][e]) < __double_as_longlong(sq) - kNearShift)
+              if (__double2hiint(acc[i][jb][e]) < __double2hiint(sq) - kNearShiftHi)
                 acc[i][jb][e] = mma_exact_r2(a.cand + rows_i[i] * (long long)a.d, a.d, a.lb, a.range, tp + (jc + e) * ds);
             }
           }
         }
       }
-      // (3) running minimum (integer pipe, r2 >= 0 here) and the weighted kernel sum, same summation order as before
+      // (3) the weighted kernel sum, same summation order as before; the running minimum only pre-tests the high
+      // words here (one integer compare per pair, r2 >= 0 so the bit patterns order like the values) ...
+      bool min_any = false;
+      int mnhi[kMmaMB];
+#pragma unroll
+      for (int i = 0; i < kMmaMB; ++i) mnhi[i] = (int)(mnb[i] >> 32);
 #pragma unroll
       for (int jb = 0; jb < kMmaJB; ++jb) {
         const double2 w2 = *reinterpret_cast<const double2*>(tw + j0 + 8 * jb + 2 * tig);
@@ -242,10 +249,19 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 <= 4 ? kMmaMinBlocks + 1 : kM
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const double r2 = acc[i][jb][e];
-            mnb[i] = min(mnb[i], __double_as_longlong(r2));
+            min_any |= __double2hiint(r2) <= mnhi[i];
             sum[i] = fma(mma_phi_from_r2<KERN>(r2), e ? w2.y : w2.x, sum[i]);
           }
         }
+      }
+      // ... (4) and is updated exactly only when some pair can lower it (ever rarer as the sweep proceeds)
+      if (min_any) {
+#pragma unroll
+        for (int jb = 0; jb < kMmaJB; ++jb)
+#pragma unroll
+          for (int i = 0; i < kMmaMB; ++i)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) mnb[i] = min(mnb[i], __double_as_longlong(acc[i][jb][e]));
       }
     }
 #if B2_MMA_EMPTY_BAR

@@ -2,8 +2,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 rm -f gpurun_out/k2x_ep.txt
-build/tune/sqrt_probe >> gpurun_out/k2x_ep.txt 2>&1
-for v in ep3 ep3_fs ep3_fs2 ep3_fs ep3_fs2; do
+for v in ep3_fs2 lean ep3_fs2 lean; do
   echo "== $v" >> gpurun_out/k2x_ep.txt
   timeout 120 build/tune/k2x_$v 1048576 20000 5 >> gpurun_out/k2x_ep.txt 2>&1
 done
