@@ -2,7 +2,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 rm -f gpurun_out/k2x_ep.txt
-for v in ep3_fs2 lean ep3_fs2 lean; do
+for v in "$@"; do
   echo "== $v" >> gpurun_out/k2x_ep.txt
   timeout 120 build/tune/k2x_$v 1048576 20000 5 >> gpurun_out/k2x_ep.txt 2>&1
 done
