@@ -254,37 +254,84 @@ __global__ void __launch_bounds__(128) trsm_right32_kernel(double* __restrict__ 
     if (c < w) row[c] = x[c];
 }
 
-// solve with the rows x rows diagonal block at (r0, r0) of the lower factor: transpose == 0: L x = y (forward),
-// transpose != 0: L^T x = y (backward).  Single CTA of 128 threads.
-__global__ void __launch_bounds__(kNB) diag_lower_solve_kernel(const double* __restrict__ A, int ld, int r0, int rows,
-                                                                const double* __restrict__ y, double* __restrict__ x,
-                                                                int transpose) {
-  extern __shared__ double s[];  // rows x (kNB + 1), s[i][k] = L[i][k] (or L^T when transposing)
-  __shared__ double sx[kNB];
+// Inverses of ALL diagonal blocks of the lower factor in one launch (CTA b inverts the block at (b kNB, b kNB)):
+// thread j builds column j of L^-1 by forward substitution out of shared memory.  With them the two triangular
+// solves need no sequential in-block substitution: a block step is a 128 x 128 matrix-vector product.
+__global__ void __launch_bounds__(kNB) block_inverse_kernel(const double* __restrict__ A, int ld, int n16,
+                                                            double* __restrict__ Linv) {
+  // one kNB x (kNB + 1) array: L in the lower triangle (diagonal included), X = L^-1 strictly below its diagonal is
+  // kept TRANSPOSED in the upper triangle (X[i][j] at s[j][i], i > j), its diagonal in sD
+  extern __shared__ double s[];
+  __shared__ double sD[kNB];
   const int st = kNB + 1, tid = threadIdx.x;
-  for (int i = 0; i < rows; ++i) {  // thread = column: coalesced row reads, no integer division
-    if (tid < rows) {
-      const double e = tid <= i ? A[(size_t)(r0 + i) * ld + r0 + tid] : 0.0;
-      if (transpose) s[tid * st + i] = e; else s[i * st + tid] = e;
-    }
-  }
-  double v = tid < rows ? y[r0 + tid] : 0.0;
+  const int r0 = blockIdx.x * kNB, rows = (n16 - r0 < kNB) ? (n16 - r0) : kNB;
+  for (int i = 0; i < rows; ++i)
+    if (tid <= i) s[i * st + tid] = A[(size_t)(r0 + i) * ld + r0 + tid];
   __syncthreads();
-  const double rdiag = tid < rows ? 1.0 / s[tid * st + tid] : 0.0;  // all reciprocals in parallel, off the critical path
-  if (!transpose) {
-    for (int k = 0; k < rows; ++k) {
-      if (tid == k) { v *= rdiag; sx[k] = v; }
-      __syncthreads();
-      if (tid > k && tid < rows) v = fma(-s[tid * st + k], sx[k], v);
-    }
-  } else {
-    for (int k = rows - 1; k >= 0; --k) {
-      if (tid == k) { v *= rdiag; sx[k] = v; }
-      __syncthreads();
-      if (tid < k) v = fma(-s[tid * st + k], sx[k], v);
+  const int j = tid;
+  if (j < rows) {
+    const double xjj = 1.0 / s[j * st + j];
+    sD[j] = xjj;
+    double* xr = s + j * st;  // xr[k] = X[k][j] for k > j
+    for (int i = j + 1; i < rows; ++i) {
+      const double* li = s + i * st;
+      double a0 = -li[j] * xjj, a1 = 0.0;
+      int k = j + 1;
+      for (; k + 1 < i; k += 2) {
+        a0 = fma(-li[k], xr[k], a0);
+        a1 = fma(-li[k + 1], xr[k + 1], a1);
+      }
+      if (k < i) a0 = fma(-li[k], xr[k], a0);
+      xr[i] = (a0 + a1) / li[i];
     }
   }
-  if (tid < rows) x[r0 + tid] = v;
+  __syncthreads();
+  double* out = Linv + (size_t)blockIdx.x * kNB * kNB;
+  for (int i = 0; i < kNB; ++i) {
+    double v = 0.0;
+    if (i < rows && tid < rows) v = tid < i ? s[tid * st + i] : (tid == i ? sD[i] : 0.0);
+    out[(size_t)i * kNB + tid] = v;
+  }
+}
+
+// x[0 .. rows) = B y (transpose == 0) or B^T y (transpose != 0) for one kNB x kNB lower-triangular block B = L_bb^-1
+__global__ void __launch_bounds__(kNB) block_matvec_kernel(const double* __restrict__ B, int rows,
+                                                           const double* __restrict__ y, double* __restrict__ x,
+                                                           int transpose) {
+  extern __shared__ double s[];  // kNB x (kNB + 1)
+  __shared__ double sy[kNB];
+  const int st = kNB + 1, tid = threadIdx.x;
+  sy[tid] = tid < rows ? y[tid] : 0.0;
+  if (!transpose) {  // row dot products: stage the block so the row walks are conflict-free
+    for (int i = 0; i < rows; ++i) s[i * st + tid] = B[(size_t)i * kNB + tid];
+    __syncthreads();
+    if (tid < rows) {
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      int k = 0;
+      for (; k + 3 <= tid; k += 4) {
+        a0 = fma(s[tid * st + k], sy[k], a0);
+        a1 = fma(s[tid * st + k + 1], sy[k + 1], a1);
+        a2 = fma(s[tid * st + k + 2], sy[k + 2], a2);
+        a3 = fma(s[tid * st + k + 3], sy[k + 3], a3);
+      }
+      for (; k <= tid; ++k) a0 = fma(s[tid * st + k], sy[k], a0);
+      x[tid] = (a0 + a1) + (a2 + a3);
+    }
+  } else {  // column dot products: the global reads are already coalesced
+    __syncthreads();
+    if (tid < rows) {
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      int i = tid;
+      for (; i + 3 < rows; i += 4) {
+        a0 = fma(B[(size_t)i * kNB + tid], sy[i], a0);
+        a1 = fma(B[(size_t)(i + 1) * kNB + tid], sy[i + 1], a1);
+        a2 = fma(B[(size_t)(i + 2) * kNB + tid], sy[i + 2], a2);
+        a3 = fma(B[(size_t)(i + 3) * kNB + tid], sy[i + 3], a3);
+      }
+      for (; i < rows; ++i) a0 = fma(B[(size_t)i * kNB + tid], sy[i], a0);
+      x[tid] = (a0 + a1) + (a2 + a3);
+    }
+  }
 }
 
 // y[c] -= sum_{r in [r0, r0+rows)} A[r][c] x[r]  for c < ccount  (thread per column: coalesced over c)
@@ -382,13 +429,14 @@ int chol_fit_weights(b200rbf_ctx* h, const double* Xu_dev, const double* f_dev, 
   const size_t oLt = take((size_t)kNB * kNB), oG = take((size_t)tp * tp), oR1 = take((size_t)tp * tp);
   const size_t oR2 = take((size_t)tp * tp), oR = take((size_t)tp * tp), oS = take((size_t)tp * tp);
   const size_t oGp = take((size_t)nparts * tp * tp), oV0 = take(n16), oV1 = take(n16), oV2 = take(n16), oq = take(tp);
+  const size_t oLi = take((size_t)((n16 + kNB - 1) / kNB) * kNB * kNB);
   B2_TRY(F.chol.reserve(need * sizeof(double)));
   B2_TRY(F.A.reserve(((size_t)n16 * ld + 1024) * sizeof(double)));
   double* base = F.chol.as<double>();
   CholWork& w = *wk;
   w.P = base + oP; w.Qneg = base + oQn; w.W = base + oW; w.Acat = base + oAc; w.Bcat = base + oBc; w.T21 = base + oT21;
   w.Lt = base + oLt; w.G = base + oG; w.R1 = base + oR1; w.R2 = base + oR2; w.R = base + oR; w.S = base + oS;
-  w.gpart = base + oGp; w.v0 = base + oV0; w.v1 = base + oV1; w.v2 = base + oV2; w.q = base + oq;
+  w.Linv = base + oLi; w.gpart = base + oGp; w.v0 = base + oV0; w.v1 = base + oV1; w.v2 = base + oV2; w.q = base + oq;
   w.n = n; w.n16 = n16; w.t = t; w.tp = tp; w.ld = ld;
   double* A = F.A.as<double>();
   double* Q = w.P;  // P is orthonormalised in place
@@ -476,18 +524,21 @@ int chol_fit_weights(b200rbf_ctx* h, const double* Xu_dev, const double* f_dev, 
   LAUNCHED(h);
   sub_q_kernel<<<(n16 + 255) / 256, 256, 0, h->stream>>>(Q, n, tp, w.q, w.v0, n16);
   LAUNCHED(h);
-  const size_t sm_diag = (size_t)kNB * (kNB + 1) * sizeof(double);
-  B2_CUDA(cudaFuncSetAttribute(diag_lower_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_diag));
+  const size_t sm_blk = (size_t)kNB * (kNB + 1) * sizeof(double);
+  B2_CUDA(cudaFuncSetAttribute(block_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_blk));
+  B2_CUDA(cudaFuncSetAttribute(block_matvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_blk));
   const int nblk = (n16 + kNB - 1) / kNB;
+  block_inverse_kernel<<<nblk, kNB, sm_blk, h->stream>>>(A, ld, n16, w.Linv);
+  LAUNCHED(h);
   for (int b = 0; b < nblk; ++b) {  // forward: L y = b   (y in v1), right-looking: every row below updates in parallel
     const int r0 = b * kNB, rows = (n16 - r0 < kNB) ? (n16 - r0) : kNB;
-    diag_lower_solve_kernel<<<1, kNB, sm_diag, h->stream>>>(A, ld, r0, rows, w.v0, w.v1, 0);
+    block_matvec_kernel<<<1, kNB, sm_blk, h->stream>>>(w.Linv + (size_t)b * kNB * kNB, rows, w.v0 + r0, w.v1 + r0, 0);
     LAUNCHED(h);
     B2_TRY(strip_gemv(h, A, ld, r0 + rows, n16 - r0 - rows, r0, r0 + rows, w.v1, w.v0));
   }
   for (int b = nblk - 1; b >= 0; --b) {  // backward: L^T x = y   (x in v2, y consumed in v1)
     const int r0 = b * kNB, rows = (n16 - r0 < kNB) ? (n16 - r0) : kNB;
-    diag_lower_solve_kernel<<<1, kNB, sm_diag, h->stream>>>(A, ld, r0, rows, w.v1, w.v2, 1);
+    block_matvec_kernel<<<1, kNB, sm_blk, h->stream>>>(w.Linv + (size_t)b * kNB * kNB, rows, w.v1 + r0, w.v2 + r0, 1);
     LAUNCHED(h);
     if (r0 > 0) {
       col_update_kernel<<<(r0 + 255) / 256, 256, 0, h->stream>>>(A, ld, r0, rows, r0, w.v2, w.v1);
