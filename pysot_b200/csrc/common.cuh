@@ -166,7 +166,7 @@ struct FitState {
 
 // views into FitState::chol for one null-space Cholesky fit
 struct CholWork {
-  double *P, *Qneg, *W, *Acat, *Bcat, *T21, *Lt, *Linv, *G, *R1, *R2, *R, *S, *gpart, *v0, *v1, *v2, *q;
+  double *P, *Qneg, *W, *Acat, *Bcat, *T21, *Linv, *LinvT, *Tn, *G, *R1, *R2, *R, *S, *gpart, *v0, *v1, *v2, *q;
   int n, n16, t, tp, ld;
 };
 

@@ -13,13 +13,14 @@
 // (rbf.py:149-153).  Both solvers are backward stable, so predictions agree to the reference's reorder noise.
 //
 // Steps (all on the handle's stream, all row-major):
-//   1. Phi + eta I -> A (n16 x ld, n16 = n rounded to 16)                                    assemble_plain
+//   1. Phi + eta I -> A (n16 x ld, n16 = n rounded to 32)                                    assemble_plain
 //   2. P = [1, Xu] (n x tp, tp = t rounded to 16), Q, R by CholeskyQR2                       gram / chol_small / apply_rinv
 //   3. W = (Phi + eta I) Q                                                                   DMMA GEMM (K = n16)
 //   4. S = Q^T W,  M = A - [Q | W | -Q (S + sigma I)] [W^T ; Q^T ; Q^T]  (lower triangle)    DMMA GEMM (K = 3 tp)
-//   5. blocked right-looking Cholesky, 128-column panels: diagonal block in one CTA's shared memory, 32-column
-//      triangular solves + DMMA GEMM for the panel, DMMA GEMM (lower tiles only) for the trailing update
-//   6. c = Pi L^-T L^-1 Pi f   (strip GEMV + 128 x 128 triangular solves)
+//   5. two-level blocked Cholesky: 128-column steps (diagonal block factored AND inverted in one CTA's shared memory,
+//      the panel below it by one DMMA GEMM with the inverse) inside 512-column outer panels whose trailing update is
+//      one lower-triangle DMMA GEMM with K = 512
+//   6. c = Pi L^-T L^-1 Pi f   (strip GEMV + 128 x 128 matrix-vector products with the diagonal-block inverses)
 //   7. lambda from step 7 of the header formula; (Phi + eta I) c is evaluated by the fused score kernel (api.cu)
 #include "common.cuh"
 
@@ -33,7 +34,8 @@ int strip_gemv(b200rbf_ctx* h, const double* A, int ld, int r0, int rows, int c0
 
 namespace {
 
-constexpr int kNB = 128;
+constexpr int kNB = 128;     // columns factored per potrf step
+constexpr int kOuter = 512;  // columns whose trailing update is applied at once (K of the big DMMA GEMM)
 
 #define LAUNCHED(h)               \
   do {                            \
@@ -189,162 +191,256 @@ __global__ void pad_identity_kernel(double* __restrict__ A, int ld, int n, int n
   A[(size_t)i * ld + j] = (i == j) ? 1.0 : 0.0;
 }
 
-// Cholesky of the nb x nb diagonal block at (j0, j0) in one CTA; writes L back (lower) and L^T into Lt (nb x kNB).
-// Right-looking, thread = (row i, column residue mod 8): three barriers per column, conflict-free shared-memory
-// walks (row stride nb + 1), no integer division in the update loop.
-constexpr int kPotrfThreads = 1024, kPotrfParts = kPotrfThreads / kNB;
-__global__ void __launch_bounds__(kPotrfThreads) potrf_kernel(double* __restrict__ A, int ld, int j0, int nb,
-                                                    double* __restrict__ Lt, int* __restrict__ info) {
-  extern __shared__ double s[];  // nb x (nb + 1)
-  const int st = nb + 1, tid = threadIdx.x;
-  const int col = tid & (kNB - 1), half = tid >> 7;  // kNB == 128; `half` = column residue class 0 .. kPotrfParts-1
-  for (int i = half; i < nb; i += kPotrfParts)
-    if (col < nb) s[i * st + col] = col <= i ? A[(size_t)(j0 + i) * ld + j0 + col] : 0.0;
-  __syncthreads();
-  const int i = col;  // this thread's row in the update phase
-  for (int k = 0; k < nb; ++k) {
-    if (tid == k) {
-      const double dgl = s[k * st + k];
-      if (!(dgl > 0.0) && *info == 0) *info = j0 + k + 1;
-      s[k * st + k] = sqrt(dgl);
-    }
-    __syncthreads();
-    if (half == 0 && i > k && i < nb) s[i * st + k] /= s[k * st + k];
-    __syncthreads();
-    if (i > k && i < nb) {
-      const double lik = s[i * st + k];
-      for (int j = k + 1 + half; j <= i; j += kPotrfParts) s[i * st + j] = fma(-lik, s[j * st + k], s[i * st + j]);
-    }
-    // the next column's pivot s[k+1][k+1] is final once row k+1's own thread(s) are done: the barrier at the top of
-    // the next iteration (after the sqrt by thread k+1) orders it for everyone else
-    __syncthreads();
-  }
-  for (int r = half; r < nb; r += kPotrfParts) {
-    if (col < nb) {
-      if (col <= r) A[(size_t)(j0 + r) * ld + j0 + col] = s[r * st + col];
-      Lt[(size_t)r * kNB + col] = col >= r ? s[col * st + r] : 0.0;  // Lt[r][c] = L[c][r]
-    }
-  }
-}
-
-// X[r0 .. r0+nrows, c0 .. c0+w) <- X L^-T with L the lower w x w diagonal block at (c0, c0); one thread per row
-__global__ void __launch_bounds__(128) trsm_right32_kernel(double* __restrict__ A, int ld, int r0, int nrows, int c0,
-                                                           int w) {
-  __shared__ double sL[32][33];
-  for (int e = threadIdx.x; e < 32 * 32; e += blockDim.x) {
-    const int i = e >> 5, k = e & 31;
-    sL[i][k] = (i < w && k <= i) ? A[(size_t)(c0 + i) * ld + c0 + k] : (i == k ? 1.0 : 0.0);
+// Cholesky of the nb x nb diagonal block at (j0, j0) (nb a multiple of 32) AND the inverse of its factor, one CTA.
+// Factorisation: right-looking with ONE barrier per column (see the loop).  Inverse by blocks of 32: the diagonal
+// sub-blocks by forward substitution in registers (warp per sub-block, lane = column), the sub-blocks at block
+// distance 1, 2, 3 from X_IJ = -X_II sum_K L_IK X_KJ.  Writes L back into A and L^-1 / L^-T (kNB x kNB, zero padded)
+// for the panel GEMM and the triangular solves.  Phase times at nb = 128 (tools/potrf_probe.cu): load 8 us,
+// factorisation ~100 us (shared-memory bound: one FMA per read-modify-write), inverse 15 us, stores 6 us.
+constexpr int kPiThreads = 512;
+__global__ void __launch_bounds__(kPiThreads) potrf_inv_kernel(double* __restrict__ A, int ld, int j0, int nb,
+                                                               double* __restrict__ Linv, double* __restrict__ LinvT,
+                                                               int* __restrict__ info) {
+  // S (kNB x (kNB + 1)): L in the lower triangle (diagonal included); X = L^-1 strictly below its diagonal is kept
+  // TRANSPOSED in the strict upper triangle (X[i][j] at S[j][i], i > j) and its diagonal is rD.  Tb: three 32 x 33
+  // scratch blocks for the partial sums T_IJ.
+  extern __shared__ double sm[];
+  __shared__ double rD[kNB];  // reciprocals of the diagonal of L = diagonal of L^-1
+  constexpr int st = kNB + 1;
+  double* S = sm;
+  double* Tb = sm + kNB * st;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int e = tid; e < kNB * kNB; e += kPiThreads) {
+    const int i = e >> 7, c = e & (kNB - 1);
+    S[i * st + c] = (i < nb && c <= i) ? A[(size_t)(j0 + i) * ld + j0 + c] : 0.0;
   }
   __syncthreads();
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= nrows) return;
-  double* row = A + (size_t)(r0 + r) * ld + c0;
-  double x[32];
+#if defined(PROBE_STOP) && PROBE_STOP == 4
+  return;
+#endif
+  const int nsub = nb / 32;
+  // ---- factorisation: right-looking, ONE barrier per column.  Column k is left unscaled while it is in use:
+  // S[i][j] -= S[i][k] S[j][k] / pivot_k needs no scaled copy, so there is no barrier between "scale" and "update";
+  // the scaling by 1 / sqrt(pivot_k) happens once at the end.  thread = (row i, column class q of 4).
+  {
+    const int i = tid & (kNB - 1), q = tid >> 7;
+    bool bad = false;
+    if (tid == 0) rD[0] = 1.0 / S[0];  // rD doubles as the "1 / pivot" mailbox during this phase
+    __syncthreads();
+    for (int k = 0; k < nb; ++k) {
+      const double rp = rD[k];  // 1 / pivot_k, published during step k - 1 by the thread that finished S[k][k]
+      bad |= !(rp > 0.0);
+      if (i > k && i < nb) {
+        const double t = S[i * st + k] * rp;
+        double* ri = S + i * st;
+        const double* ck = S + k;
+        int j = k + 1 + q;
+        if (i == k + 1 && q == 0) {  // this update finishes the next pivot: publish its reciprocal off the critical path
+          const double pv = fma(-t, ck[(k + 1) * st], ri[k + 1]);
+          ri[k + 1] = pv;
+          rD[k + 1] = 1.0 / pv;
+          j += kPiThreads / kNB;
+        }
+        // batches of 8: all loads (indices clamped to i, so they are unconditional), then the FMAs, then the stores;
+        // written with conditional loads the compiler interleaves load / FMA / store per element and the latencies add up
+        constexpr int JS = kPiThreads / kNB;
+        for (; j <= i; j += 8 * JS) {
+          double c[8], r[8];
 #pragma unroll
-  for (int c = 0; c < 32; ++c) x[c] = c < w ? row[c] : 0.0;
+          for (int u = 0; u < 8; ++u) {
+            const int jj = min(j + u * JS, i);
+            c[u] = ck[jj * st];
+            r[u] = ri[jj];
+          }
 #pragma unroll
-  for (int c = 0; c < 32; ++c) {
-    double v = x[c];
+          for (int u = 0; u < 8; ++u) r[u] = fma(-t, c[u], r[u]);
 #pragma unroll
-    for (int k = 0; k < c; ++k) v = fma(-x[k], sL[c][k], v);
-    x[c] = v / sL[c][c];
-  }
-#pragma unroll
-  for (int c = 0; c < 32; ++c)
-    if (c < w) row[c] = x[c];
-}
-
-// Inverses of ALL diagonal blocks of the lower factor in one launch (CTA b inverts the block at (b kNB, b kNB)):
-// thread j builds column j of L^-1 by forward substitution out of shared memory.  With them the two triangular
-// solves need no sequential in-block substitution: a block step is a 128 x 128 matrix-vector product.
-__global__ void __launch_bounds__(kNB) block_inverse_kernel(const double* __restrict__ A, int ld, int n16,
-                                                            double* __restrict__ Linv) {
-  // one kNB x (kNB + 1) array: L in the lower triangle (diagonal included), X = L^-1 strictly below its diagonal is
-  // kept TRANSPOSED in the upper triangle (X[i][j] at s[j][i], i > j), its diagonal in sD
-  extern __shared__ double s[];
-  __shared__ double sD[kNB];
-  const int st = kNB + 1, tid = threadIdx.x;
-  const int r0 = blockIdx.x * kNB, rows = (n16 - r0 < kNB) ? (n16 - r0) : kNB;
-  for (int i = 0; i < rows; ++i)
-    if (tid <= i) s[i * st + tid] = A[(size_t)(r0 + i) * ld + r0 + tid];
-  __syncthreads();
-  const int j = tid;
-  if (j < rows) {
-    const double xjj = 1.0 / s[j * st + j];
-    sD[j] = xjj;
-    double* xr = s + j * st;  // xr[k] = X[k][j] for k > j
-    for (int i = j + 1; i < rows; ++i) {
-      const double* li = s + i * st;
-      double a0 = -li[j] * xjj, a1 = 0.0;
-      int k = j + 1;
-      for (; k + 1 < i; k += 2) {
-        a0 = fma(-li[k], xr[k], a0);
-        a1 = fma(-li[k + 1], xr[k + 1], a1);
+          for (int u = 0; u < 8; ++u)
+            if (j + u * JS <= i) ri[j + u * JS] = r[u];
+        }
       }
-      if (k < i) a0 = fma(-li[k], xr[k], a0);
-      xr[i] = (a0 + a1) / li[i];
+      __syncthreads();
     }
+    // scale: L[i][k] = S[i][k] / sqrt(pivot_k), L[k][k] = sqrt(pivot_k)
+    if (tid < nb) {
+      const double dg = S[tid * st + tid];
+      if (!(dg > 0.0) || dg > 1.7e308) bad = true;  // zero, negative, NaN or overflowed pivot
+      rD[tid] = 1.0 / sqrt(dg);
+    }
+    if (bad && *info == 0) *info = j0 + 1;
+    __syncthreads();
+    for (int e = tid; e < kNB * kNB; e += kPiThreads) {
+      const int r = e >> 7, c = e & (kNB - 1);
+      if (r < nb && c <= r) S[r * st + c] = (c == r) ? S[r * st + r] * rD[r] : S[r * st + c] * rD[c];
+    }
+    __syncthreads();
+  }
+#if defined(PROBE_STOP) && PROBE_STOP == 1
+  return;
+#endif
+  // ---- inverse, diagonal sub-blocks
+  if (warp < nsub) {
+    const int cI = 32 * warp;
+    double x[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      double a = (i == lane) ? 1.0 : 0.0;
+      const double* li = S + (cI + i) * st + cI;
+#pragma unroll
+      for (int k = 0; k < i; ++k) a = fma(-li[k], x[k], a);  // x[k] == 0 for k < lane
+      x[i] = (i >= lane) ? a * rD[cI + i] : 0.0;
+    }
+#pragma unroll
+    for (int i = 1; i < 32; ++i)
+      if (i > lane) S[(cI + lane) * st + cI + i] = x[i];  // X[cI + i][cI + lane]
   }
   __syncthreads();
-  double* out = Linv + (size_t)blockIdx.x * kNB * kNB;
-  for (int i = 0; i < kNB; ++i) {
-    double v = 0.0;
-    if (i < rows && tid < rows) v = tid < i ? s[tid * st + i] : (tid == i ? sD[i] : 0.0);
-    out[(size_t)i * kNB + tid] = v;
+#if defined(PROBE_STOP) && PROBE_STOP == 2
+  return;
+#endif
+  // ---- inverse, off-diagonal sub-blocks by block distance
+  for (int dlt = 1; dlt < nsub; ++dlt) {
+    const int cnt = (nsub - dlt) * 1024;
+    for (int e = tid; e < cnt; e += kPiThreads) {  // T_IJ[r][c] = sum_kk L[cI + r][kk] X[kk][cJ + c], kk in [cJ + c, cI)
+      const int J = e >> 10, r = (e >> 5) & 31, c = e & 31, I = J + dlt;
+      const int cI = 32 * I, col = 32 * J + c;
+      const double* lr = S + (cI + r) * st;
+      const double* xc = S + col * st;  // xc[kk] = X[kk][col] for kk > col
+      double a0 = lr[col] * rD[col], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      int kk = col + 1;
+      for (; kk + 3 < cI; kk += 4) {
+        a0 = fma(lr[kk], xc[kk], a0);
+        a1 = fma(lr[kk + 1], xc[kk + 1], a1);
+        a2 = fma(lr[kk + 2], xc[kk + 2], a2);
+        a3 = fma(lr[kk + 3], xc[kk + 3], a3);
+      }
+      for (; kk < cI; ++kk) a0 = fma(lr[kk], xc[kk], a0);
+      Tb[J * (32 * 33) + c * 33 + r] = (a0 + a1) + (a2 + a3);
+    }
+    __syncthreads();
+    for (int e = tid; e < cnt; e += kPiThreads) {  // X_IJ = -X_II T_IJ
+      const int J = e >> 10, r = (e >> 5) & 31, c = e & 31, I = J + dlt;
+      const int cI = 32 * I, col = 32 * J + c;
+      const double* tc = Tb + J * (32 * 33) + c * 33;
+      const double* xr = S + cI * st + cI + r;  // xr[k * st] = X[cI + r][cI + k] for k < r
+      double a0 = rD[cI + r] * tc[r], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      int k = 0;
+      for (; k + 3 < r; k += 4) {
+        a0 = fma(xr[k * st], tc[k], a0);
+        a1 = fma(xr[(k + 1) * st], tc[k + 1], a1);
+        a2 = fma(xr[(k + 2) * st], tc[k + 2], a2);
+        a3 = fma(xr[(k + 3) * st], tc[k + 3], a3);
+      }
+      for (; k < r; ++k) a0 = fma(xr[k * st], tc[k], a0);
+      S[col * st + cI + r] = -((a0 + a1) + (a2 + a3));  // X[cI + r][col]
+    }
+    __syncthreads();
+  }
+#if defined(PROBE_STOP) && PROBE_STOP == 3
+  return;
+#endif
+  for (int e = tid; e < kNB * kNB; e += kPiThreads) {
+    const int i = e >> 7, c = e & (kNB - 1);
+    const bool in = i < nb && c < nb;
+    if (in && c <= i) A[(size_t)(j0 + i) * ld + j0 + c] = S[i * st + c];
+    double v = 0.0, vt = 0.0;
+    if (in) {
+      if (c < i) v = S[c * st + i];        // Linv[i][c] = X[i][c]
+      else if (c > i) vt = S[i * st + c];  // LinvT[i][c] = X[c][i]
+      else v = vt = rD[i];
+    }
+    Linv[e] = v;
+    LinvT[e] = vt;
   }
 }
 
-// x[0 .. rows) = B y (transpose == 0) or B^T y (transpose != 0) for one kNB x kNB lower-triangular block B = L_bb^-1
-__global__ void __launch_bounds__(kNB) block_matvec_kernel(const double* __restrict__ B, int rows,
-                                                           const double* __restrict__ y, double* __restrict__ x,
-                                                           int transpose) {
+// after the panel GEMM Tn = -L21 (rows x nb, leading dimension kNB): A21 <- L21 and T21 <- L21^T (nb x rows, leading
+// dimension ldt), the B operand of the trailing updates
+__global__ void finish_panel_kernel(const double* __restrict__ Tn, int rows, int nb, double* __restrict__ A21, int ld,
+                                    double* __restrict__ T21, int ldt) {
+  __shared__ double tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+    const int r = r0 + dy, c = c0 + threadIdx.x;
+    double v = 0.0;
+    if (r < rows && c < nb) {
+      v = Tn[(size_t)r * kNB + c];
+      A21[(size_t)r * ld + c] = -v;
+    }
+    tile[dy][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+    const int c = c0 + dy, r = r0 + threadIdx.x;
+    if (c < nb && r < rows) T21[(size_t)c * ldt + r] = -tile[threadIdx.x][dy];
+  }
+}
+
+// x[0 .. rows) = B y (transpose == 0) or B^T y (transpose != 0) for one kNB x kNB lower-triangular block B = L_bb^-1.
+// 512 threads: thread (o = tid & 127, part = tid >> 7) sums a quarter of output o's terms, the quarters meet in
+// shared memory.  The block is staged through shared memory so that both walks are conflict-free and every global
+// read is coalesced and issued up front.
+constexpr int kMvThreads = 512, kMvParts = kMvThreads / kNB;
+__global__ void __launch_bounds__(kMvThreads) block_matvec_kernel(const double* __restrict__ B, int rows,
+                                                                  const double* __restrict__ y, double* __restrict__ x,
+                                                                  int transpose) {
   extern __shared__ double s[];  // kNB x (kNB + 1)
   __shared__ double sy[kNB];
-  const int st = kNB + 1, tid = threadIdx.x;
-  sy[tid] = tid < rows ? y[tid] : 0.0;
-  if (!transpose) {  // row dot products: stage the block so the row walks are conflict-free
-    for (int i = 0; i < rows; ++i) s[i * st + tid] = B[(size_t)i * kNB + tid];
-    __syncthreads();
-    if (tid < rows) {
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-      int k = 0;
-      for (; k + 3 <= tid; k += 4) {
-        a0 = fma(s[tid * st + k], sy[k], a0);
-        a1 = fma(s[tid * st + k + 1], sy[k + 1], a1);
-        a2 = fma(s[tid * st + k + 2], sy[k + 2], a2);
-        a3 = fma(s[tid * st + k + 3], sy[k + 3], a3);
+  __shared__ double sp[kMvParts][kNB];
+  const int st = kNB + 1, tid = threadIdx.x, o = tid & (kNB - 1), part = tid >> 7;
+  if (tid < kNB) sy[tid] = tid < rows ? y[tid] : 0.0;
+  for (int i = part; i < rows; i += kMvParts) s[i * st + o] = B[(size_t)i * kNB + o];
+  __syncthreads();
+  double a0 = 0.0, a1 = 0.0;
+  if (o < rows) {
+    if (!transpose) {  // x[o] = sum_{k <= o} B[o][k] y[k]
+      int k = part;
+      for (; k + kMvParts <= o; k += 2 * kMvParts) {
+        a0 = fma(s[o * st + k], sy[k], a0);
+        a1 = fma(s[o * st + k + kMvParts], sy[k + kMvParts], a1);
       }
-      for (; k <= tid; ++k) a0 = fma(s[tid * st + k], sy[k], a0);
-      x[tid] = (a0 + a1) + (a2 + a3);
-    }
-  } else {  // column dot products: the global reads are already coalesced
-    __syncthreads();
-    if (tid < rows) {
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-      int i = tid;
-      for (; i + 3 < rows; i += 4) {
-        a0 = fma(B[(size_t)i * kNB + tid], sy[i], a0);
-        a1 = fma(B[(size_t)(i + 1) * kNB + tid], sy[i + 1], a1);
-        a2 = fma(B[(size_t)(i + 2) * kNB + tid], sy[i + 2], a2);
-        a3 = fma(B[(size_t)(i + 3) * kNB + tid], sy[i + 3], a3);
+      if (k <= o) a0 = fma(s[o * st + k], sy[k], a0);
+    } else {  // x[o] = sum_{i >= o} B[i][o] y[i]
+      int i = o + part;
+      for (; i + kMvParts < rows; i += 2 * kMvParts) {
+        a0 = fma(s[i * st + o], sy[i], a0);
+        a1 = fma(s[(i + kMvParts) * st + o], sy[i + kMvParts], a1);
       }
-      for (; i < rows; ++i) a0 = fma(B[(size_t)i * kNB + tid], sy[i], a0);
-      x[tid] = (a0 + a1) + (a2 + a3);
+      if (i < rows) a0 = fma(s[i * st + o], sy[i], a0);
     }
   }
+  sp[part][o] = a0 + a1;
+  __syncthreads();
+  if (tid < rows) x[tid] = (sp[0][tid] + sp[1][tid]) + (sp[2][tid] + sp[3][tid]);
 }
 
-// y[c] -= sum_{r in [r0, r0+rows)} A[r][c] x[r]  for c < ccount  (thread per column: coalesced over c)
-__global__ void col_update_kernel(const double* __restrict__ A, int ld, int r0, int rows, int ccount,
-                                  const double* __restrict__ x, double* __restrict__ y) {
+// y[c] -= sum_{r in [r0, r0+rows)} A[r][c] x[r]  for c < ccount.  CTA = 32 columns x 8 row groups: coalesced over c,
+// each thread walks rows / 8 rows, the groups meet in shared memory.
+__global__ void __launch_bounds__(256) col_update_kernel(const double* __restrict__ A, int ld, int r0, int rows, int ccount,
+                                                         const double* __restrict__ x, double* __restrict__ y) {
   __shared__ double sx[kNB];
-  if (threadIdx.x < rows) sx[threadIdx.x] = x[r0 + threadIdx.x];
+  __shared__ double sp[8][33];
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  if (tid < kNB) sx[tid] = tid < rows ? x[r0 + tid] : 0.0;
   __syncthreads();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= ccount) return;
-  double s = 0.0;
-  for (int r = 0; r < rows; ++r) s = fma(A[(size_t)(r0 + r) * ld + c], sx[r], s);
-  y[c] -= s;
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double a0 = 0.0, a1 = 0.0;
+  if (c < ccount) {
+    int r = threadIdx.y;
+    for (; r + 8 < rows; r += 16) {
+      a0 = fma(A[(size_t)(r0 + r) * ld + c], sx[r], a0);
+      a1 = fma(A[(size_t)(r0 + r + 8) * ld + c], sx[r + 8], a1);
+    }
+    if (r < rows) a0 = fma(A[(size_t)(r0 + r) * ld + c], sx[r], a0);
+  }
+  sp[threadIdx.y][threadIdx.x] = a0 + a1;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < ccount) {
+    double t = 0.0;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t += sp[g][threadIdx.x];
+    y[c] -= t;
+  }
 }
 
 // out[c] = sum_i Q[i][c] v[i]  (c < tp); one CTA of 1024 threads
@@ -420,23 +516,24 @@ int gram(b200rbf_ctx* h, const double* X, const double* Y, int n, int tp, double
 int chol_fit_weights(b200rbf_ctx* h, const double* Xu_dev, const double* f_dev, int n, int d, int kernel, double eta,
                      CholWork* wk, int* info_dev) {
   FitState& F = h->fit;
-  const int t = d + 1, tp = (t + 15) & ~15, n16 = (n + 15) & ~15, ld = n16;
+  const int t = d + 1, tp = (t + 15) & ~15, n16 = (n + 31) & ~31, ld = n16;  // n16: padded to the 32-column sub-blocks
   const int nparts = (n + 63) / 64;
   size_t need = 0;
   auto take = [&](size_t cnt) { size_t off = need; need += (cnt + 15) & ~(size_t)15; return off; };
   const size_t oP = take((size_t)n16 * tp), oQn = take((size_t)n16 * tp), oW = take((size_t)n16 * tp);
-  const size_t oAc = take((size_t)n16 * 3 * tp), oBc = take((size_t)3 * tp * ld), oT21 = take((size_t)kNB * ld);
-  const size_t oLt = take((size_t)kNB * kNB), oG = take((size_t)tp * tp), oR1 = take((size_t)tp * tp);
+  const size_t oAc = take((size_t)n16 * 3 * tp), oBc = take((size_t)3 * tp * ld), oT21 = take((size_t)kOuter * ld);
+  const size_t oG = take((size_t)tp * tp), oR1 = take((size_t)tp * tp);
   const size_t oR2 = take((size_t)tp * tp), oR = take((size_t)tp * tp), oS = take((size_t)tp * tp);
   const size_t oGp = take((size_t)nparts * tp * tp), oV0 = take(n16), oV1 = take(n16), oV2 = take(n16), oq = take(tp);
-  const size_t oLi = take((size_t)((n16 + kNB - 1) / kNB) * kNB * kNB);
+  const size_t oLi = take((size_t)((n16 + kNB - 1) / kNB) * kNB * kNB), oLiT = take((size_t)kNB * kNB);
+  const size_t oTn = take((size_t)n16 * kNB);
   B2_TRY(F.chol.reserve(need * sizeof(double)));
   B2_TRY(F.A.reserve(((size_t)n16 * ld + 1024) * sizeof(double)));
   double* base = F.chol.as<double>();
   CholWork& w = *wk;
   w.P = base + oP; w.Qneg = base + oQn; w.W = base + oW; w.Acat = base + oAc; w.Bcat = base + oBc; w.T21 = base + oT21;
-  w.Lt = base + oLt; w.G = base + oG; w.R1 = base + oR1; w.R2 = base + oR2; w.R = base + oR; w.S = base + oS;
-  w.Linv = base + oLi; w.gpart = base + oGp; w.v0 = base + oV0; w.v1 = base + oV1; w.v2 = base + oV2; w.q = base + oq;
+  w.G = base + oG; w.R1 = base + oR1; w.R2 = base + oR2; w.R = base + oR; w.S = base + oS;
+  w.Linv = base + oLi; w.LinvT = base + oLiT; w.Tn = base + oTn; w.gpart = base + oGp; w.v0 = base + oV0; w.v1 = base + oV1; w.v2 = base + oV2; w.q = base + oq;
   w.n = n; w.n16 = n16; w.t = t; w.tp = tp; w.ld = ld;
   double* A = F.A.as<double>();
   double* Q = w.P;  // P is orthonormalised in place
@@ -492,30 +589,37 @@ int chol_fit_weights(b200rbf_ctx* h, const double* Xu_dev, const double* f_dev, 
     pad_identity_kernel<<<(cnt + 255) / 256, 256, 0, h->stream>>>(A, ld, n, n16);
     LAUNCHED(h);
   }
-  // 5. blocked Cholesky of the n16 x n16 lower triangle
-  const size_t sm_potrf = (size_t)kNB * (kNB + 1) * sizeof(double);
-  B2_CUDA(cudaFuncSetAttribute(potrf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_potrf));
-  for (int j0 = 0; j0 < n16; j0 += kNB) {
-    const int nb = (n16 - j0 < kNB) ? (n16 - j0) : kNB;
-    potrf_kernel<<<1, kPotrfThreads, (size_t)nb * (nb + 1) * sizeof(double), h->stream>>>(A, ld, j0, nb, w.Lt, info_dev);
-    LAUNCHED(h);
-    const int r0 = j0 + nb, rows = n16 - r0;
-    if (rows <= 0) break;
-    for (int s0 = 0; s0 < nb; s0 += 32) {
-      const int wdt = (nb - s0 < 32) ? (nb - s0) : 32;
-      trsm_right32_kernel<<<(rows + 127) / 128, 128, 0, h->stream>>>(A, ld, r0, rows, j0 + s0, wdt);
+  // 5. blocked Cholesky of the n16 x n16 lower triangle, two levels.  Per 128-column step: potrf_inv_kernel factors
+  // the diagonal block and inverts its factor; the panel below becomes ONE DMMA GEMM  Tn = 0 - A21 L11^-T  (no
+  // sequential triangular solve over the long dimension); finish_panel_kernel stores L21 and L21^T; only the columns
+  // that remain inside the current kOuter-wide outer panel are updated right away.  Everything to the right of the
+  // outer panel is updated once per outer panel with K = kOuter: the DMMA GEMM runs at 32.8 TFLOP/s with K = 512
+  // against 27.3 with K = 128 (C is read and written once per 512 instead of once per 128 columns).
+  // The inverses of the diagonal blocks are kept for step 6.
+  const size_t sm_pi = ((size_t)kNB * (kNB + 1) + 3 * 32 * 33) * sizeof(double);
+  B2_CUDA(cudaFuncSetAttribute(potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pi));
+  for (int J0 = 0; J0 < n16; J0 += kOuter) {
+    const int R0 = (J0 + kOuter < n16) ? J0 + kOuter : n16;  // first column right of the outer panel
+    for (int j0 = J0; j0 < R0; j0 += kNB) {
+      const int nb = (n16 - j0 < kNB) ? (n16 - j0) : kNB;
+      const int r0 = j0 + nb, rows = n16 - r0;
+      potrf_inv_kernel<<<1, kPiThreads, sm_pi, h->stream>>>(A, ld, j0, nb, w.Linv + (size_t)(j0 / kNB) * kNB * kNB,
+                                                            w.LinvT, info_dev);
       LAUNCHED(h);
-      const int rest = nb - s0 - wdt;
-      if (rest > 0)  // A21[:, s0+w:] -= X[:, s0:s0+w] * (L11[s0+w:, s0:s0+w])^T  with the transposed block taken from Lt
-        B2_TRY(gemm_sub_ex(h, A + (size_t)r0 * ld + j0 + s0 + wdt, ld, A + (size_t)r0 * ld + j0 + s0, ld,
-                           w.Lt + (size_t)s0 * kNB + s0 + wdt, kNB, rows, rest, wdt, 0));
-    }
-    {
+      if (rows <= 0) break;
+      double* A21 = A + (size_t)r0 * ld + j0;
+      double* T21 = w.T21 + (size_t)(j0 - J0) * ld + r0;  // T21[k][r - r0] = L[r][j0 + k]
+      B2_CUDA(cudaMemsetAsync(w.Tn, 0, (size_t)rows * kNB * sizeof(double), h->stream));
+      B2_TRY(gemm_sub_ex(h, w.Tn, kNB, A21, ld, w.LinvT, kNB, rows, nb, nb, 0));
       dim3 blk(32, 8), grd((nb + 31) / 32, (rows + 31) / 32);
-      transpose_kernel<<<grd, blk, 0, h->stream>>>(A + (size_t)r0 * ld + j0, rows, nb, ld, w.T21, ld);  // L21^T
+      finish_panel_kernel<<<grd, blk, 0, h->stream>>>(w.Tn, rows, nb, A21, ld, T21, ld);
       LAUNCHED(h);
+      if (r0 < R0)  // the rest of the outer panel: rows >= r0, columns [r0, R0)
+        B2_TRY(gemm_sub_ex(h, A + (size_t)r0 * ld + r0, ld, A21, ld, T21, ld, rows, R0 - r0, nb, 1));
     }
-    B2_TRY(gemm_sub_ex(h, A + (size_t)r0 * ld + r0, ld, A + (size_t)r0 * ld + j0, ld, w.T21, ld, rows, rows, nb, 1));
+    if (R0 < n16)  // everything right of the outer panel, K = R0 - J0
+      B2_TRY(gemm_sub_ex(h, A + (size_t)R0 * ld + R0, ld, A + (size_t)R0 * ld + J0, ld, w.T21 + R0, ld, n16 - R0, n16 - R0,
+                         R0 - J0, 1));
   }
   // 6. c = Pi L^-T L^-1 Pi f
   copy_pad_kernel<<<(n16 + 255) / 256, 256, 0, h->stream>>>(f_dev, n, w.v0, n16);
@@ -525,23 +629,20 @@ int chol_fit_weights(b200rbf_ctx* h, const double* Xu_dev, const double* f_dev, 
   sub_q_kernel<<<(n16 + 255) / 256, 256, 0, h->stream>>>(Q, n, tp, w.q, w.v0, n16);
   LAUNCHED(h);
   const size_t sm_blk = (size_t)kNB * (kNB + 1) * sizeof(double);
-  B2_CUDA(cudaFuncSetAttribute(block_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_blk));
   B2_CUDA(cudaFuncSetAttribute(block_matvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_blk));
   const int nblk = (n16 + kNB - 1) / kNB;
-  block_inverse_kernel<<<nblk, kNB, sm_blk, h->stream>>>(A, ld, n16, w.Linv);
-  LAUNCHED(h);
   for (int b = 0; b < nblk; ++b) {  // forward: L y = b   (y in v1), right-looking: every row below updates in parallel
     const int r0 = b * kNB, rows = (n16 - r0 < kNB) ? (n16 - r0) : kNB;
-    block_matvec_kernel<<<1, kNB, sm_blk, h->stream>>>(w.Linv + (size_t)b * kNB * kNB, rows, w.v0 + r0, w.v1 + r0, 0);
+    block_matvec_kernel<<<1, kMvThreads, sm_blk, h->stream>>>(w.Linv + (size_t)b * kNB * kNB, rows, w.v0 + r0, w.v1 + r0, 0);
     LAUNCHED(h);
     B2_TRY(strip_gemv(h, A, ld, r0 + rows, n16 - r0 - rows, r0, r0 + rows, w.v1, w.v0));
   }
   for (int b = nblk - 1; b >= 0; --b) {  // backward: L^T x = y   (x in v2, y consumed in v1)
     const int r0 = b * kNB, rows = (n16 - r0 < kNB) ? (n16 - r0) : kNB;
-    block_matvec_kernel<<<1, kNB, sm_blk, h->stream>>>(w.Linv + (size_t)b * kNB * kNB, rows, w.v1 + r0, w.v2 + r0, 1);
+    block_matvec_kernel<<<1, kMvThreads, sm_blk, h->stream>>>(w.Linv + (size_t)b * kNB * kNB, rows, w.v1 + r0, w.v2 + r0, 1);
     LAUNCHED(h);
     if (r0 > 0) {
-      col_update_kernel<<<(r0 + 255) / 256, 256, 0, h->stream>>>(A, ld, r0, rows, r0, w.v2, w.v1);
+      col_update_kernel<<<(r0 + 31) / 32, dim3(32, 8), 0, h->stream>>>(A, ld, r0, rows, r0, w.v2, w.v1);
       LAUNCHED(h);
     }
   }

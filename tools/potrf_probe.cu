@@ -1,0 +1,63 @@
+// Times potrf_inv_kernel (fit_chol.cu) on one 128 x 128 SPD block, whole and with phases cut off (-DPROBE_STOP=n is
+// honoured by the kernel when compiled from this file), and checks L L^T = A and L^-1 L = I.
+#include <cstdio>
+#include <vector>
+#include <cmath>
+#include "../pysot_b200/csrc/fit_chol.cu"
+namespace b200rbf {
+int gemm_sub_ex(b200rbf_ctx*, double*, int, const double*, int, const double*, int, int, int, int, int) { return 0; }
+int assemble_plain(b200rbf_ctx*, const double*, int, int, int, double, double*, int, int) { return 0; }
+int strip_gemv(b200rbf_ctx*, const double*, int, int, int, int, int, const double*, double*) { return 0; }
+}
+namespace b200rbf { void set_error(const char*, ...) {} }
+using namespace b200rbf;
+int main() {
+  const int nb = 128, ld = 128;
+  std::vector<double> A(nb * nb), G(nb * nb);
+  srand(1);
+  for (auto& v : G) v = rand() / (double)RAND_MAX - 0.5;
+  for (int i = 0; i < nb; ++i)
+    for (int j = 0; j < nb; ++j) {
+      double s = (i == j) ? 4.0 : 0.0;
+      for (int k = 0; k < nb; ++k) s += G[i * nb + k] * G[j * nb + k];
+      A[i * nb + j] = s;
+    }
+  double *dA, *dA0, *dLi, *dLiT; int* dinfo;
+  cudaMalloc(&dA, nb * nb * 8); cudaMalloc(&dA0, nb * nb * 8); cudaMalloc(&dLi, nb * nb * 8); cudaMalloc(&dLiT, nb * nb * 8);
+  cudaMalloc(&dinfo, 4); cudaMemset(dinfo, 0, 4);
+  cudaMemcpy(dA0, A.data(), nb * nb * 8, cudaMemcpyHostToDevice);
+  const size_t sm_pi = ((size_t)kNB * (kNB + 1) + 3 * 32 * 33) * sizeof(double);
+  cudaFuncSetAttribute(potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pi);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float best = 1e9;
+  for (int rep = 0; rep < 20; ++rep) {
+    cudaMemcpy(dA, dA0, nb * nb * 8, cudaMemcpyDeviceToDevice);
+    cudaEventRecord(e0);
+    potrf_inv_kernel<<<1, kPiThreads, sm_pi>>>(dA, ld, 0, nb, dLi, dLiT, dinfo);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
+  }
+  std::vector<double> L(nb * nb), Li(nb * nb), LiT(nb * nb); int info = -1;
+  cudaMemcpy(L.data(), dA, nb * nb * 8, cudaMemcpyDeviceToHost);
+  cudaMemcpy(Li.data(), dLi, nb * nb * 8, cudaMemcpyDeviceToHost);
+  cudaMemcpy(LiT.data(), dLiT, nb * nb * 8, cudaMemcpyDeviceToHost);
+  cudaMemcpy(&info, dinfo, 4, cudaMemcpyDeviceToHost);
+  double e_f = 0, e_i = 0, e_t = 0;
+  for (int i = 0; i < nb; ++i)
+    for (int j = 0; j <= i; ++j) {
+      double s = 0, t = 0;
+      for (int k = 0; k <= j; ++k) s += L[i * nb + k] * L[j * nb + k];
+      for (int k = j; k <= i; ++k) t += Li[i * nb + k] * L[k * nb + j];
+      e_f = fmax(e_f, fabs(s - A[i * nb + j]));
+      e_i = fmax(e_i, fabs(t - (i == j ? 1.0 : 0.0)));
+      e_t = fmax(e_t, fabs(LiT[j * nb + i] - Li[i * nb + j]));
+    }
+  printf("potrf_inv_kernel stop=%d: %.1f us  info=%d  |LL^T-A| %.2e  |L^-1 L - I| %.2e  |LinvT - Linv^T| %.2e  (%s)\n",
+#ifdef PROBE_STOP
+         PROBE_STOP,
+#else
+         0,
+#endif
+         best * 1e3, info, e_f, e_i, e_t, cudaGetErrorString(cudaGetLastError()));
+  return 0;
+}
