@@ -339,7 +339,7 @@ def run_native(args, rank, world, local_rank):
     roofline = {
         "kernel": "score_mma_kernel<K4=13, cubic> (norm-expansion distances, DMMA dot products, near pairs recomputed)",
         "bound": "tensor", "bound_detail": "FP64: DMMA (fp64 tensor op) and DFMA share one datapath on sm_100a (measured: "
-                                           "36.5 vs 36.6 TFLOP/s, 36.0 interleaved); the bf16 tensor peak does not apply, HBM is at 4 %",
+                                           "36.5 vs 36.6 TFLOP/s, 36.0 interleaved); the bf16 tensor peak does not apply; HBM traffic is < 0.1 % of its peak",
         "achieved": k_tflops,
         "peak": peaks["dfma_tflops"], "unit": "TFLOP/s", "frac": k_tflops / peaks["dfma_tflops"],
         "peak_source": "b200rbf_fp64_peaks: dependency-free DFMA loop on this device, 300 ms (MEASURED_PEAKS.json has no fp64 entry)",
