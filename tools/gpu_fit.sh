@@ -1,4 +1,5 @@
 #!/bin/bash
+# fit-focused check: the fit / Cholesky parity tests, N = 20000 timing, ncu launch list of an N = 5000 fit
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 600 -p no:cacheprovider -k "cholesky or fit or golden or scale or capped or interpolates" > gpurun_out/pytest_fit.log 2>&1

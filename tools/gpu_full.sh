@@ -1,4 +1,5 @@
 #!/bin/bash
+# full single-GPU check under gpurun: parity suite, smoke, bench, ncu launch lists of the bench and of one N = 20000 fit
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 timeout 1800 python -m pytest tests -m gpu -q --timeout 900 -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1

@@ -1,4 +1,5 @@
 #!/bin/bash
+# runs the named build/tune/k2x_<variant> binaries (tools/k2x_tune.cu builds of score_mma.cuh) on the bench shape
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 rm -f gpurun_out/k2x_ep.txt
