@@ -71,7 +71,7 @@ __global__ void split_coef_kernel(const double* __restrict__ c, int t, int n, do
 }
 // centers with row stride ds and their squared norms (operands of score_mma_kernel)
 __global__ void mma_points_kernel(const double* __restrict__ src, int n, int d, double* __restrict__ dst, int npad,
-                                  int ds, double* __restrict__ cnorm) {
+                                  int ds, double* __restrict__ cnorm, double* __restrict__ aug) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npad) return;
   const int si = i < n ? i : n - 1;
@@ -82,6 +82,11 @@ __global__ void mma_points_kernel(const double* __restrict__ src, int n, int d, 
     n2 = fma(v, v, n2);
   }
   cnorm[i] = n2;
+  if (aug != nullptr) {  // the augmented copy: slots d and d + 1 carry 1 and |c|^2
+    for (int k = 0; k < ds; ++k) aug[(size_t)i * ds + k] = dst[(size_t)i * ds + k];
+    aug[(size_t)i * ds + d] = 1.0;
+    aug[(size_t)i * ds + d + 1] = n2;
+  }
 }
 __global__ void negate_stats_kernel(const double* __restrict__ s, double* __restrict__ out) {
   if (threadIdx.x == 0) {
@@ -132,8 +137,11 @@ int install_model(b200rbf_ctx* h, const double* Xu_dev, const double* c_dev, int
     M.ds = mma_stride(d);
     B2_TRY(M.centers_x.reserve((size_t)M.npad * M.ds * sizeof(double)));
     B2_TRY(M.cnorm.reserve((size_t)M.npad * sizeof(double)));
+    M.aug = (d % 4 == 1 || d % 4 == 2);  // two free slots in the last k-step of the DMMA kernel
+    if (M.aug) B2_TRY(M.centers_m.reserve((size_t)M.npad * M.ds * sizeof(double)));
     mma_points_kernel<<<(M.npad + 127) / 128, 128, 0, h->stream>>>(Xu_dev, n, d, M.centers_x.as<double>(), M.npad, M.ds,
-                                                                  M.cnorm.as<double>());
+                                                                  M.cnorm.as<double>(),
+                                                                  M.aug ? M.centers_m.as<double>() : nullptr);
     h->launches++;
     B2_CUDA(cudaGetLastError());
   }
@@ -193,7 +201,8 @@ int launch_score_mma(b200rbf_ctx* h, const ScoreArgs& a) {
   const Model& M = h->model;
   MmaArgs ma;
   ma.s = a;
-  ma.s.pts = M.centers_x.as<double>();
+  ma.aug = M.aug;
+  ma.s.pts = M.aug ? M.centers_m.as<double>() : M.centers_x.as<double>();
   ma.cnorm = M.cnorm.as<double>();
   ma.ds = M.ds;
   const int k4 = (M.d + 3) / 4;
@@ -393,7 +402,7 @@ int b200rbf_destroy(b200rbf_handle h) {
   cudaStreamSynchronize(h->copy_stream);
   Model& M = h->model;
   M.centers.release(); M.centersT.release(); M.coef.release(); M.tailc.release();
-  M.centers_x.release(); M.cnorm.release();
+  M.centers_x.release(); M.centers_m.release(); M.cnorm.release();
   ScoreState& S = h->score;
   S.cand_own.release(); S.fvals.release(); S.dmerit.release(); S.parts.release(); S.pair_parts.release();
   S.stats.release(); S.winner.release(); S.results.release(); S.dist.release(); S.box.release();

@@ -133,8 +133,10 @@ struct Model {
   DevBuf coef;      // npad RBF weights (pad = 0)
   DevBuf tailc;     // ntail tail coefficients (lambda_0, lambda_1..d)
   int npadT = 0;
-  // operands of the DMMA score kernel (score_mma.cuh): centers shifted by 0.5, row stride ds, and their squared norms
+  // operands of the DMMA score kernel (score_mma.cuh): centers with row stride ds and their squared norms
   DevBuf centers_x, cnorm;
+  DevBuf centers_m;         // the same with (1, |c|^2) in slots d, d + 1 when `aug`
+  bool aug = false;
   int ds = 0;
 };
 

@@ -38,9 +38,6 @@ constexpr int kMmaMinBlocks = B2_MMA_MINB; // CTAs per SM the register budget is
                                            // tools/k2x_tune.cu sweep: 2 x 4 beats 2 x 3 by 6 %, 4 x 2 by 16 % at d = 50
 constexpr int kMmaTileRows = 8 * kMmaJB;   // center rows per tile
 static_assert(32 % kMmaTileRows == 0, "pad_rows() pads the center rows to multiples of 32: tiles must divide that");
-#ifndef B2_MMA_EMPTY_BAR
-#define B2_MMA_EMPTY_BAR 0
-#endif
 #ifndef B2_MMA_STAGES
 #define B2_MMA_STAGES 3
 #endif
@@ -50,6 +47,7 @@ constexpr int kMmaRowsPerCta = (kMmaThreads / 32) * 8 * kMmaMB;
 struct MmaArgs {
   ScoreArgs s;          // pts = shifted centers (npad x ds), coef = weights, as in score_kernel
   const double* cnorm;  // npad squared norms of the shifted centers
+  bool aug;             // centers carry (1, |c|^2) in slots d, d + 1 (see score_mma_kernel)
   int ds;               // center row stride in doubles (== 4 mod 16, >= 4 * K4)
 };
 
@@ -101,7 +99,10 @@ static __device__ __noinline__ double mma_exact_r2(const double* __restrict__ sr
   return acc;
 }
 
-template <int K4, int KERN>
+// AUG (usable when d + 2 <= 4 K4, i.e. d mod 4 is 1 or 2): the two unused slots of the last k-step carry the norms --
+// A row = (-2 u, |u|^2, 1), B row = (c, 1, |c|^2) -- so the MMA accumulates r^2 itself and pass 1 needs no FP64
+// instruction at all; the near test then compares against 2^-10 max(|u|^2, |c|^2) (integer max of the high words).
+template <int K4, int KERN, bool AUG>
 __global__ void __launch_bounds__(kMmaThreads, (K4 <= 4 ? kMmaMinBlocks + 1 : kMmaMinBlocks)) score_mma_kernel(MmaArgs ma) {
   const ScoreArgs& a = ma.s;
   const int ds = ma.ds;
@@ -110,8 +111,7 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 <= 4 ? kMmaMinBlocks + 1 : kM
   double* s_wts = s_pts + (size_t)kMmaStages * kMmaTileRows * ds;          // [stages][rows]
   double* s_nrm = s_wts + kMmaStages * kMmaTileRows;                       // [stages][rows]
   uint64_t* s_full = reinterpret_cast<uint64_t*>(s_nrm + kMmaStages * kMmaTileRows);
-  uint64_t* s_empty = s_full + kMmaStages;                               // consumer release, one arrival per warp
-  double* s_red = reinterpret_cast<double*>(s_empty + kMmaStages);        // 4 x warps
+  double* s_red = reinterpret_cast<double*>(s_full + kMmaStages);         // 4 x warps
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gid = lane >> 2, tig = lane & 3;
@@ -119,10 +119,7 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 <= 4 ? kMmaMinBlocks + 1 : kM
   const int ntiles = (a.npad + kMmaTileRows - 1) / kMmaTileRows;
 
   if (tid == 0) {
-    for (int s = 0; s < kMmaStages; ++s) {
-      mbar_init(&s_full[s], 1);
-      mbar_init(&s_empty[s], kMmaThreads / 32);
-    }
+    for (int s = 0; s < kMmaStages; ++s) mbar_init(&s_full[s], 1);
     fence_barrier_init();
   }
   __syncthreads();
@@ -156,12 +153,19 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 <= 4 ? kMmaMinBlocks + 1 : kM
         v = __ldg(src + dim);
         if (a.lb != nullptr) v = __ddiv_rn(__dsub_rn(v, __ldg(a.lb + dim)), __ldg(a.range + dim));
       }
-      afr[i][k] = v;
+      afr[i][k] = AUG ? -2.0 * v : v;
       n2 = fma(v, v, n2);
     }
     n2 += __shfl_xor_sync(0xffffffffu, n2, 1);
     n2 += __shfl_xor_sync(0xffffffffu, n2, 2);
     nx[i] = n2;
+    if (AUG) {
+#pragma unroll
+      for (int k = 0; k < K4; ++k) {
+        if (4 * k + tig == a.d) afr[i][k] = n2;
+        if (4 * k + tig == a.d + 1) afr[i][k] = 1.0;
+      }
+    }
   }
 
   const double inf = __longlong_as_double(0x7ff0000000000000LL);
@@ -212,10 +216,15 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 <= 4 ? kMmaMinBlocks + 1 : kM
         for (int i = 0; i < kMmaMB; ++i) {
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            const double sq = nx[i] + (e ? n2.y : n2.x);
-            const double r2 = fma(-2.0, acc[i][jb][e], sq);
-            near_any |= __double2hiint(r2) < __double2hiint(sq) - kNearShiftHi;
-            acc[i][jb][e] = r2;
+            if (AUG) {
+              near_any |= __double2hiint(acc[i][jb][e]) <
+                          max(__double2hiint(nx[i]), __double2hiint(e ? n2.y : n2.x)) - kNearShiftHi;
+            } else {
+              const double sq = nx[i] + (e ? n2.y : n2.x);
+              const double r2 = fma(-2.0, acc[i][jb][e], sq);
+              near_any |= __double2hiint(r2) < __double2hiint(sq) - kNearShiftHi;
+              acc[i][jb][e] = r2;
+            }
           }
         }
       }
@@ -228,8 +237,9 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 <= 4 ? kMmaMinBlocks + 1 : kM
           for (int i = 0; i < kMmaMB; ++i) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-              const double sq = nx[i] + tn[jc + e];
-              if (__double2hiint(acc[i][jb][e]) < __double2hiint(sq) - kNearShiftHi)
+              const int thr = AUG ? max(__double2hiint(nx[i]), __double2hiint(tn[jc + e]))
+                                  : __double2hiint(nx[i] + tn[jc + e]);
+              if (__double2hiint(acc[i][jb][e]) < thr - kNearShiftHi)
                 acc[i][jb][e] = mma_exact_r2(a.cand + rows_i[i] * (long long)a.d, a.d, a.lb, a.range, tp + (jc + e) * ds);
             }
           }
@@ -264,19 +274,8 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 <= 4 ? kMmaMinBlocks + 1 : kM
             for (int e = 0; e < 2; ++e) mnb[i] = min(mnb[i], __double_as_longlong(acc[i][jb][e]));
       }
     }
-#if B2_MMA_EMPTY_BAR
-    // no CTA-wide barrier in the main loop: each warp releases the stage, the producer thread waits for all four
-    // releases before refilling it, the other warps run ahead by up to the ring depth
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&s_empty[s]);
-    if (tid == 0 && t + kMmaStages < ntiles) {
-      mbar_wait(&s_empty[s], (uint32_t)((t / kMmaStages) & 1));
-      issue(t + kMmaStages);
-    }
-#else
     __syncthreads();
     if (tid == 0 && t + kMmaStages < ntiles) issue(t + kMmaStages);
-#endif
   }
 
   // combine the quad's partial results (fixed order: deterministic)
@@ -301,6 +300,7 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 <= 4 ? kMmaMinBlocks + 1 : kM
     }
     ts += __shfl_xor_sync(0xffffffffu, ts, 1);
     ts += __shfl_xor_sync(0xffffffffu, ts, 2);
+    if (AUG) ts *= -0.5;  // the fragments hold -2 u (exact scaling)
     const long long row = base + gid + 8 * i;
     const bool live = row < a.m;
     const double fval = sum[i] + (ts + __ldg(a.tailc));
@@ -351,13 +351,13 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 <= 4 ? kMmaMinBlocks + 1 : kM
 }
 
 inline size_t score_mma_smem_bytes(int ds) {
-  return ((size_t)kMmaStages * kMmaTileRows * ds + 2 * (size_t)kMmaStages * kMmaTileRows + 2 * kMmaStages +
+  return ((size_t)kMmaStages * kMmaTileRows * ds + 2 * (size_t)kMmaStages * kMmaTileRows + kMmaStages +
           4 * (kMmaThreads / 32)) * 8;
 }
 
-template <int K4, int KERN>
+template <int K4, int KERN, bool AUG>
 int launch_score_mma_inst(b200rbf_ctx* h, const MmaArgs& ma) {
-  auto kern = score_mma_kernel<K4, KERN>;
+  auto kern = score_mma_kernel<K4, KERN, AUG>;
   const size_t smem = score_mma_smem_bytes(ma.ds);
   B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (ma.s.occ_out != nullptr) {
@@ -374,9 +374,15 @@ int launch_score_mma_inst(b200rbf_ctx* h, const MmaArgs& ma) {
 template <int K4>
 int launch_score_mma_k4(b200rbf_ctx* h, const MmaArgs& ma, int kernel) {
   switch (kernel) {
-    case B200RBF_KERNEL_CUBIC: return launch_score_mma_inst<K4, B200RBF_KERNEL_CUBIC>(h, ma);
-    case B200RBF_KERNEL_TPS: return launch_score_mma_inst<K4, B200RBF_KERNEL_TPS>(h, ma);
-    default: return launch_score_mma_inst<K4, B200RBF_KERNEL_LINEAR>(h, ma);
+    case B200RBF_KERNEL_CUBIC:
+      return ma.aug ? launch_score_mma_inst<K4, B200RBF_KERNEL_CUBIC, true>(h, ma)
+                    : launch_score_mma_inst<K4, B200RBF_KERNEL_CUBIC, false>(h, ma);
+    case B200RBF_KERNEL_TPS:
+      return ma.aug ? launch_score_mma_inst<K4, B200RBF_KERNEL_TPS, true>(h, ma)
+                    : launch_score_mma_inst<K4, B200RBF_KERNEL_TPS, false>(h, ma);
+    default:
+      return ma.aug ? launch_score_mma_inst<K4, B200RBF_KERNEL_LINEAR, true>(h, ma)
+                    : launch_score_mma_inst<K4, B200RBF_KERNEL_LINEAR, false>(h, ma);
   }
 }
 

@@ -3,6 +3,9 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <vector>
+#ifndef TUNE_AUG
+#define TUNE_AUG false
+#endif
 #include "../pysot_b200/csrc/score_mma.cuh"
 namespace b200rbf {
 void set_error(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vfprintf(stderr, fmt, ap); va_end(ap); fputc('\n', stderr); }
@@ -21,7 +24,7 @@ int main(int argc, char** argv) {
   std::vector<double> hc((size_t)m * d), hp((size_t)npad * ds, 0.0), hw(npad), hn(npad), ht(d + 1, 0.1), hb(2 * pad_dim(d));
   srand(1);
   for (auto& v : hc) v = rand() / (double)RAND_MAX;
-  for (int i = 0; i < npad; ++i) { double s = 0; for (int k = 0; k < d; ++k) { double v = rand() / (double)RAND_MAX; hp[(size_t)i * ds + k] = v; s += v * v; } hn[i] = s; hw[i] = rand() / (double)RAND_MAX - 0.5; }
+  for (int i = 0; i < npad; ++i) { double s = 0; for (int k = 0; k < d; ++k) { double v = rand() / (double)RAND_MAX; hp[(size_t)i * ds + k] = v; s += v * v; } hn[i] = s; if (TUNE_AUG) { hp[(size_t)i * ds + d] = 1.0; hp[(size_t)i * ds + d + 1] = s; } hw[i] = rand() / (double)RAND_MAX - 0.5; }
   for (int k = 0; k < pad_dim(d); ++k) { hb[k] = 0.0; hb[pad_dim(d) + k] = 1.0; }
   double *cand, *pts, *coef, *nrm, *tailc, *box, *fv, *dm, *parts;
   const int nparts = (int)((m + kMmaRowsPerCta - 1) / kMmaRowsPerCta);
@@ -37,9 +40,9 @@ int main(int argc, char** argv) {
   ScoreArgs& a = ma.s;
   a.cand = cand; a.m = m; a.d = d; a.lb = box; a.range = box + pad_dim(d); a.pts = pts; a.coef = coef; a.tailc = tailc;
   a.npad = npad; a.tail = 0; a.dscale = 1.0; a.min_mode = 1; a.fvals = fv; a.dmerit = dm; a.parts = parts; a.nparts = nparts;
-  ma.cnorm = nrm; ma.ds = ds;
+  ma.cnorm = nrm; ma.ds = ds; ma.aug = TUNE_AUG;
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-  auto run = [&]() { return launch_score_mma_inst<K4, 0>(&ctx, ma); };
+  auto run = [&]() { return launch_score_mma_inst<K4, 0, TUNE_AUG>(&ctx, ma); };
   for (int i = 0; i < 2; ++i) if (run() != 0) return 1;
   CK(cudaStreamSynchronize(ctx.stream));
   float best = 1e30f;
@@ -47,8 +50,8 @@ int main(int argc, char** argv) {
     CK(cudaEventRecord(e0, ctx.stream)); if (run() != 0) return 1; CK(cudaEventRecord(e1, ctx.stream)); CK(cudaEventSynchronize(e1));
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); best = ms < best ? ms : best;
   }
-  int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, score_mma_kernel<K4, 0>, kMmaThreads, score_mma_smem_bytes(ds));
-  cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, score_mma_kernel<K4, 0>);
+  int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, score_mma_kernel<K4, 0, TUNE_AUG>, kMmaThreads, score_mma_smem_bytes(ds));
+  cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, score_mma_kernel<K4, 0, TUNE_AUG>);
   const double pairs = (double)m * n;
   printf("mma d=%d mb=%d minb=%d jb=%d regs=%d ctas/sm=%d  best %.3f ms  %.4e pairs/s  %.2f TFLOP/s at %d flops/pair\n", d, kMmaMB,
          kMmaMinBlocks, kMmaJB, fa.numRegs, occ, best, pairs / (best * 1e-3), pairs * (3.0 * d + 6) / (best * 1e-3) / 1e12, 3 * d + 6);
