@@ -191,6 +191,17 @@ __global__ void pad_identity_kernel(double* __restrict__ A, int ld, int n, int n
   A[(size_t)i * ld + j] = (i == j) ? 1.0 : 0.0;
 }
 
+// 1 / x for the pivots: hardware seed (MUFU.RCP64H, ~2^-20) + two Newton steps = 4 dependent FMAs.  The IEEE division
+// is ~10 dependent FP64 operations, and this value heads the critical path of every column of the factorisation.
+// A non-positive or non-finite pivot yields a value that fails the `> 0` test downstream (inf, negative or NaN).
+__device__ __forceinline__ double fast_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  y = fma(fma(-x, y, 1.0), y, y);
+  y = fma(fma(-x, y, 1.0), y, y);
+  return y;
+}
+
 // Cholesky of the nb x nb diagonal block at (j0, j0) (nb a multiple of 32) AND the inverse of its factor, one CTA.
 // Factorisation: right-looking with ONE barrier per column (see the loop).  Inverse by blocks of 32: the diagonal
 // sub-blocks by forward substitution in registers (warp per sub-block, lane = column), the sub-blocks at block
@@ -219,47 +230,86 @@ __global__ void __launch_bounds__(kPiThreads) potrf_inv_kernel(double* __restric
   return;
 #endif
   const int nsub = nb / 32;
-  // ---- factorisation: right-looking, ONE barrier per column.  Column k is left unscaled while it is in use:
-  // S[i][j] -= S[i][k] S[j][k] / pivot_k needs no scaled copy, so there is no barrier between "scale" and "update";
-  // the scaling by 1 / sqrt(pivot_k) happens once at the end.  thread = (row i, column class q of 4).
+  // ---- factorisation: right-looking in panels of 32 columns.  thread = (row i, column group q): for the duration of a
+  // panel it keeps its 8 entries S[i][c0 + 8 q .. + 7] in REGISTERS.  Per column k the owners of that column publish
+  // it (still unscaled) through a double-buffered shared-memory vector -- ONE barrier per column -- and every thread
+  // applies  S[i][j] -= S[i][k] S[j][k] / pivot_k  to its registers: per column a warp issues ~10 broadcast reads
+  // instead of the ~48 shared-memory wavefronts of a read-modify-write sweep (measured: the sweep made this phase
+  // shared-memory bound, ~1000 cycles per column against a ~250-cycle dependency chain).  After the panel the rest of
+  // the block gets its rank-32 update from 4 x 4 register tiles (rows / columns interleaved so that lanes walk
+  // consecutive rows: conflict-free; 8 shared-memory reads per 16 FMAs).  The scaling by 1 / sqrt(pivot_k) happens
+  // once at the end; meanwhile rD holds the reciprocal pivots.
   {
+    __shared__ double colbuf[2][kNB];
     const int i = tid & (kNB - 1), q = tid >> 7;
     bool bad = false;
-    if (tid == 0) rD[0] = 1.0 / S[0];  // rD doubles as the "1 / pivot" mailbox during this phase
-    __syncthreads();
-    for (int k = 0; k < nb; ++k) {
-      const double rp = rD[k];  // 1 / pivot_k, published during step k - 1 by the thread that finished S[k][k]
-      bad |= !(rp > 0.0);
-      if (i > k && i < nb) {
-        const double t = S[i * st + k] * rp;
-        double* ri = S + i * st;
-        const double* ck = S + k;
-        int j = k + 1 + q;
-        if (i == k + 1 && q == 0) {  // this update finishes the next pivot: publish its reciprocal off the critical path
-          const double pv = fma(-t, ck[(k + 1) * st], ri[k + 1]);
-          ri[k + 1] = pv;
-          rD[k + 1] = 1.0 / pv;
-          j += kPiThreads / kNB;
-        }
-        // batches of 8: all loads (indices clamped to i, so they are unconditional), then the FMAs, then the stores;
-        // written with conditional loads the compiler interleaves load / FMA / store per element and the latencies add up
-        constexpr int JS = kPiThreads / kNB;
-        for (; j <= i; j += 8 * JS) {
-          double c[8], r[8];
+    for (int c0 = 0; c0 < nb; c0 += 32) {
+      const int cend = c0 + 32;
+      double reg[8];
+      double* mine = S + i * st + c0 + 8 * q;
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int jj = min(j + u * JS, i);
-            c[u] = ck[jj * st];
-            r[u] = ri[jj];
+      for (int c = 0; c < 8; ++c) reg[c] = mine[c];
+      for (int k8 = 0; k8 < 4; ++k8) {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const int k = c0 + 8 * k8 + kk;
+          double* cb = colbuf[kk & 1];
+          if (q == k8 && i >= k) cb[i] = reg[kk];
+          __syncthreads();  // also orders the reads of step k - 1 before the writes of step k + 1 into the same buffer
+          const double piv = cb[k];
+          bad |= !(piv > 0.0);
+          const double rp = fast_rcp(piv);
+          if (i == k && q == k8) rD[k] = rp;
+          if (i > k && i < nb && q >= k8) {
+            const double t = cb[i] * rp;
+            const double* cj = cb + c0 + 8 * q;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              if (q > k8 || c > kk) reg[c] = fma(-t, cj[c], reg[c]);
           }
-#pragma unroll
-          for (int u = 0; u < 8; ++u) r[u] = fma(-t, c[u], r[u]);
-#pragma unroll
-          for (int u = 0; u < 8; ++u)
-            if (j + u * JS <= i) ri[j + u * JS] = r[u];
         }
       }
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (c0 + 8 * q + c <= i) mine[c] = reg[c];
       __syncthreads();
+      // rank-32 update of the m x m block right of / below the panel: i = ti + (m/4) u, j = tj + (m/4) v
+      const int m = nb - cend;
+      if (m > 0) {
+        const int q4 = m / 4;
+        for (int t = tid; t < q4 * q4; t += kPiThreads) {
+          const int ti = t % q4, tj = t / q4;
+          const double* pi = S + (cend + ti) * st + c0;
+          const double* pj = S + (cend + tj) * st + c0;
+          double acc[4][4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
+#pragma unroll 4
+          for (int k = 0; k < 32; ++k) {
+            const double rp = rD[c0 + k];
+            double ai[4], bj[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              ai[u] = pi[u * q4 * st + k] * rp;
+              bj[u] = pj[u * q4 * st + k];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+              for (int v = 0; v < 4; ++v) acc[u][v] = fma(ai[u], bj[v], acc[u][v]);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              const int ii = ti + q4 * u, jj = tj + q4 * v;
+              if (jj <= ii) S[(cend + ii) * st + cend + jj] -= acc[u][v];
+            }
+        }
+        __syncthreads();
+      }
     }
     // scale: L[i][k] = S[i][k] / sqrt(pivot_k), L[k][k] = sqrt(pivot_k)
     if (tid < nb) {
