@@ -203,11 +203,13 @@ __device__ __forceinline__ double fast_rcp(double x) {
 }
 
 // Cholesky of the nb x nb diagonal block at (j0, j0) (nb a multiple of 32) AND the inverse of its factor, one CTA.
-// Factorisation: right-looking with ONE barrier per column (see the loop).  Inverse by blocks of 32: the diagonal
-// sub-blocks by forward substitution in registers (warp per sub-block, lane = column), the sub-blocks at block
-// distance 1, 2, 3 from X_IJ = -X_II sum_K L_IK X_KJ.  Writes L back into A and L^-1 / L^-T (kNB x kNB, zero padded)
-// for the panel GEMM and the triangular solves.  Phase times at nb = 128 (tools/potrf_probe.cu): load 8 us,
-// factorisation ~100 us (shared-memory bound: one FMA per read-modify-write), inverse 15 us, stores 6 us.
+// Factorisation: right-looking in 32-column panels held in registers, ONE barrier per column, rank-32 register-tiled
+// updates between panels (see the loop).  Inverse by blocks of 32: the diagonal sub-blocks by forward substitution in
+// registers (warp per sub-block, lane = column), the sub-blocks at block distance 1, 2, 3 from
+// X_IJ = -X_II sum_K L_IK X_KJ with 4 x 4 register tiles.  Writes L back into A and L^-1 / L^-T (kNB x kNB, zero
+// padded) for the panel GEMM and the triangular solves.  Phase times at nb = 128 (tools/potrf_probe.cu): load 8 us,
+// factorisation 36 us, inverse 24 us, stores 8 us; the first version (three barriers per column, whole-block
+// rank-1 sweeps through shared memory) took 125 us for the factorisation alone.
 constexpr int kPiThreads = 512;
 __global__ void __launch_bounds__(kPiThreads) potrf_inv_kernel(double* __restrict__ A, int ld, int j0, int nb,
                                                                double* __restrict__ Linv, double* __restrict__ LinvT,
@@ -221,6 +223,7 @@ __global__ void __launch_bounds__(kPiThreads) potrf_inv_kernel(double* __restric
   double* S = sm;
   double* Tb = sm + kNB * st;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll 8
   for (int e = tid; e < kNB * kNB; e += kPiThreads) {
     const int i = e >> 7, c = e & (kNB - 1);
     S[i * st + c] = (i < nb && c <= i) ? A[(size_t)(j0 + i) * ld + j0 + c] : 0.0;
@@ -348,41 +351,86 @@ __global__ void __launch_bounds__(kPiThreads) potrf_inv_kernel(double* __restric
 #if defined(PROBE_STOP) && PROBE_STOP == 2
   return;
 #endif
-  // ---- inverse, off-diagonal sub-blocks by block distance
+  // ---- inverse, off-diagonal sub-blocks by block distance: T_IJ = sum_{K = J}^{I - 1} L_IK X_KJ, X_IJ = -X_II T_IJ.
+  // 64 threads per 32 x 32 block, each with a 4 x 4 register tile (rows tr + 8 u, columns tc + 8 v: lanes walk
+  // consecutive rows / columns of the padded array, conflict-free): 8 shared-memory reads per 16 FMAs.  One output per
+  // thread (3 reads per FMA) was shared-memory bound at ~23 us for the whole phase.
   for (int dlt = 1; dlt < nsub; ++dlt) {
-    const int cnt = (nsub - dlt) * 1024;
-    for (int e = tid; e < cnt; e += kPiThreads) {  // T_IJ[r][c] = sum_kk L[cI + r][kk] X[kk][cJ + c], kk in [cJ + c, cI)
-      const int J = e >> 10, r = (e >> 5) & 31, c = e & 31, I = J + dlt;
-      const int cI = 32 * I, col = 32 * J + c;
-      const double* lr = S + (cI + r) * st;
-      const double* xc = S + col * st;  // xc[kk] = X[kk][col] for kk > col
-      double a0 = lr[col] * rD[col], a1 = 0.0, a2 = 0.0, a3 = 0.0;
-      int kk = col + 1;
-      for (; kk + 3 < cI; kk += 4) {
-        a0 = fma(lr[kk], xc[kk], a0);
-        a1 = fma(lr[kk + 1], xc[kk + 1], a1);
-        a2 = fma(lr[kk + 2], xc[kk + 2], a2);
-        a3 = fma(lr[kk + 3], xc[kk + 3], a3);
+    const int J = tid >> 6, tr = tid & 7, tc = (tid & 63) >> 3;
+    const bool act = J < nsub - dlt;
+    const int cI = 32 * (J + dlt), cJ = 32 * J;
+    double acc[4][4];
+    if (act) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
+      double rdc[4];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) rdc[v] = rD[cJ + tc + 8 * v];
+      // K = J: X_JJ is lower triangular -- X[kk][col] = 0 above the diagonal, 1 / L[col][col] on it
+#pragma unroll 2
+      for (int kk = cJ; kk < cJ + 32; ++kk) {
+        double l[4], x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) l[u] = S[(cI + tr + 8 * u) * st + kk];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const int col = cJ + tc + 8 * v;
+          const double raw = S[col * st + kk];
+          x[v] = kk > col ? raw : (kk == col ? rdc[v] : 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int v = 0; v < 4; ++v) acc[u][v] = fma(l[u], x[v], acc[u][v]);
       }
-      for (; kk < cI; ++kk) a0 = fma(lr[kk], xc[kk], a0);
-      Tb[J * (32 * 33) + c * 33 + r] = (a0 + a1) + (a2 + a3);
+#pragma unroll 2
+      for (int kk = cJ + 32; kk < cI; ++kk) {
+        double l[4], x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) l[u] = S[(cI + tr + 8 * u) * st + kk];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) x[v] = S[(cJ + tc + 8 * v) * st + kk];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int v = 0; v < 4; ++v) acc[u][v] = fma(l[u], x[v], acc[u][v]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) Tb[J * (32 * 33) + (tc + 8 * v) * 33 + tr + 8 * u] = acc[u][v];
     }
     __syncthreads();
-    for (int e = tid; e < cnt; e += kPiThreads) {  // X_IJ = -X_II T_IJ
-      const int J = e >> 10, r = (e >> 5) & 31, c = e & 31, I = J + dlt;
-      const int cI = 32 * I, col = 32 * J + c;
-      const double* tc = Tb + J * (32 * 33) + c * 33;
-      const double* xr = S + cI * st + cI + r;  // xr[k * st] = X[cI + r][cI + k] for k < r
-      double a0 = rD[cI + r] * tc[r], a1 = 0.0, a2 = 0.0, a3 = 0.0;
-      int k = 0;
-      for (; k + 3 < r; k += 4) {
-        a0 = fma(xr[k * st], tc[k], a0);
-        a1 = fma(xr[(k + 1) * st], tc[k + 1], a1);
-        a2 = fma(xr[(k + 2) * st], tc[k + 2], a2);
-        a3 = fma(xr[(k + 3) * st], tc[k + 3], a3);
+    if (act) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
+      double rdr[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) rdr[u] = rD[cI + tr + 8 * u];
+#pragma unroll 2
+      for (int k = 0; k < 32; ++k) {
+        double xi[4], t[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = tr + 8 * u;
+          const double raw = S[(cI + k) * st + cI + r];  // X[cI + r][cI + k] for k < r
+          xi[u] = k < r ? raw : (k == r ? rdr[u] : 0.0);
+        }
+#pragma unroll
+        for (int v = 0; v < 4; ++v) t[v] = Tb[J * (32 * 33) + (tc + 8 * v) * 33 + k];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int v = 0; v < 4; ++v) acc[u][v] = fma(xi[u], t[v], acc[u][v]);
       }
-      for (; k < r; ++k) a0 = fma(xr[k * st], tc[k], a0);
-      S[col * st + cI + r] = -((a0 + a1) + (a2 + a3));  // X[cI + r][col]
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) S[(cJ + tc + 8 * v) * st + cI + tr + 8 * u] = -acc[u][v];  // X[cI + r][cJ + c]
     }
     __syncthreads();
   }
