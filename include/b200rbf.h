@@ -45,7 +45,8 @@ enum {
   /* 1: squared distances use separate multiply and add, sequentially over the coordinates -- bit-identical
    *    to scipy's cdist (rbf.py:181, candidate_srbf.py:35).  0 (default): fused multiply-add.           */
   B200RBF_OPT_EXACT_DIST = 1,
-  /* rows per host->device chunk of the candidate pipeline (default 65536)                              */
+  /* rows per host->device chunk of the candidate pipeline for PAGEABLE host candidates (default 131072, rounded to
+   *    whole waves of the score kernel); pinned host candidates use chunks that grow geometrically from one wave  */
   B200RBF_OPT_CHUNK_ROWS = 2,
   /* LU panel width (default 128; multiple of 32)                                                       */
   B200RBF_OPT_LU_PANEL = 3,
