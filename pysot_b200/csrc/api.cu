@@ -202,6 +202,16 @@ int launch_score_mma(b200rbf_ctx* h, const ScoreArgs& a) {
   MmaArgs ma;
   ma.s = a;
   ma.aug = M.aug;
+  ma.tps_table = nullptr;
+  if (M.kernel == B200RBF_KERNEL_TPS) {
+    if (h->tps_table.p == nullptr) {  // once per handle: the half-log table of the thin-plate-spline epilogue
+      double host[2 * kTpsLogEntries];
+      tps_log_table_host(host);
+      B2_TRY(h->tps_table.reserve(sizeof(host)));
+      B2_CUDA(cudaMemcpy(h->tps_table.p, host, sizeof(host), cudaMemcpyHostToDevice));
+    }
+    ma.tps_table = h->tps_table.as<double2>();
+  }
   ma.s.pts = M.aug ? M.centers_m.as<double>() : M.centers_x.as<double>();
   ma.cnorm = M.cnorm.as<double>();
   ma.ds = M.ds;
@@ -419,6 +429,7 @@ int b200rbf_destroy(b200rbf_handle h) {
   FitState& F = h->fit;
   F.A.release(); F.piv.release(); F.rhs.release(); F.work.release(); F.flags.release(); F.chol.release();
   h->tmp_in.release(); h->tmp_out.release(); h->tmp_box.release(); h->gen_buf.release(); h->gen_pin.release();
+  h->tps_table.release();
   h->stage[0].release(); h->stage[1].release(); h->pin_small.release();
   for (int i = 0; i < 2; ++i) cudaEventDestroy(h->ev_copy[i]);
   cudaEventDestroy(h->ev_t0); cudaEventDestroy(h->ev_t1); cudaEventDestroy(h->ev_done);

@@ -189,6 +189,7 @@ struct b200rbf_ctx {
   bool lu_lookahead = false;  // implemented and correct, but measured to give no overlap (see include/b200rbf.h)
   int gemm_stages = 4;          // DMMA GEMM variant: 2 / 3 = cp.async stages at BK 16, 4 = 2 stages at BK 32 (default)
   bool gemm_stages_auto = true; // drop to 2 while a look-ahead panel shares the SMs
+  b200rbf::DevBuf tps_table;  // half-log table of the DMMA score kernel's thin-plate-spline epilogue (score_mma.cuh)
   b200rbf::PinBuf stage[2];
   b200rbf::PinBuf pin_small;
   long long launches = 0;

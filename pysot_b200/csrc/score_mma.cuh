@@ -48,6 +48,7 @@ struct MmaArgs {
   ScoreArgs s;          // pts = shifted centers (npad x ds), coef = weights, as in score_kernel
   const double* cnorm;  // npad squared norms of the shifted centers
   bool aug;             // centers carry (1, |c|^2) in slots d, d + 1 (see score_mma_kernel)
+  const double2* tps_table;  // kTpsLogEntries x (inv_j, -0.5 log inv_j), device memory (thin-plate spline only)
   int ds;               // center row stride in doubles (== 4 mod 16, >= 4 * K4)
 };
 
@@ -55,6 +56,45 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
                : "+d"(d0), "+d"(d1)
                : "d"(a), "d"(b));
+}
+
+// ---- thin-plate spline: phi = r^2 log r = c * (0.5 log c), c = r^2.  The 0.5 log c comes from a 128-entry table
+// instead of log() (~30 dependent FP64 instructions): c = 2^e m with m in [sqrt(1/2), sqrt(2)); the top 7 fraction bits
+// pick a centre m_j with a short reciprocal inv_j (10 significant bits); t = m inv_j - 1 (one FMA, |t| <= 2^-7.9);
+//   0.5 log c = e (0.5 ln 2) + (-0.5 log inv_j) + 0.5 log1p(t),   log1p by a degree-7 polynomial (truncation 2e-18).
+// 10 FP64 operations, two table words fetched with one LDS.128.  tools/log_probe.cu measures it against 0.5 * log().
+constexpr int kTpsLogEntries = 128;
+
+// host: table[j] = (inv_j, -0.5 log inv_j) for fraction index j; j >= kTpsLogSplit belongs to m / 2 in [sqrt(1/2), 1)
+constexpr int kTpsLogSplit = 53;  // fraction index of 1.4140625: from there on m is halved and e incremented
+inline void tps_log_table_host(double* out /* 2 * kTpsLogEntries */) {
+  for (int j = 0; j < kTpsLogEntries; ++j) {
+    double mj = 1.0 + (j + 0.5) / kTpsLogEntries;
+    if (j >= kTpsLogSplit) mj *= 0.5;
+    const double inv = ldexp(nearbyint(ldexp(1.0 / mj, 10)), -10);  // 10 fraction bits: m * inv is exact in the FMA
+    out[2 * j] = inv;
+    out[2 * j + 1] = (double)(-0.5L * logl((long double)inv));
+  }
+}
+
+__device__ __forceinline__ double tps_half_log(double c, const double2* __restrict__ tab) {
+  const int hi = __double2hiint(c);
+  const int j = (hi >> 13) & (kTpsLogEntries - 1);
+  const int up = j >= kTpsLogSplit;                                   // m in [sqrt 2, 2): use m / 2, e + 1
+  const int e = (hi >> 20) - 1023 + up;
+  const double m = __hiloint2double((hi & 0x000fffff) | (up ? 0x3fe00000 : 0x3ff00000), __double2loint(c));
+  const double2 tj = tab[j];
+  const double t = fma(m, tj.x, -1.0);
+  // 0.5 log1p(t) = t (1/2 - t/4 + t^2/6 - t^3/8 + t^4/10 - t^5/12 + t^6/14)
+  double q = fma(t, 1.0 / 14.0, -1.0 / 12.0);
+  q = fma(t, q, 1.0 / 10.0);
+  q = fma(t, q, -1.0 / 8.0);
+  q = fma(t, q, 1.0 / 6.0);
+  q = fma(t, q, -1.0 / 4.0);
+  q = fma(t, q, 0.5);
+  // e as a double without the (slow) integer conversion: 2^52 + 2^31 + e has e in its low word
+  const double ed = __hiloint2double(0x43300000, (int)(0x80000000u + (unsigned)e)) - 4503601774854144.0;
+  return fma(ed, 0.34657359027997264, fma(t, q, tj.y));
 }
 
 #ifndef B2_MMA_FAST_SQRT
@@ -66,7 +106,13 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 // (within one ulp) -- five FP64 operations, and, unlike sqrt(), no slow-path call, so the 16 chains of a thread sit in
 // one basic block and interleave.  0 selects sqrt().
 template <int KERN>
-__device__ __forceinline__ double mma_phi_from_r2(double r2) {
+__device__ __forceinline__ double mma_phi_from_r2(double r2, const double2* __restrict__ tps_tab) {
+  if (KERN == B200RBF_KERNEL_TPS) {
+    // tps_kernel.py:28-29 clamps r to eps; here the HIGH WORD of c = r^2 is clamped to that of eps^2 = 2^-104, which
+    // keeps log finite at r = 0; below the clamp phi is ~1e-30 either way
+    const double c = __hiloint2double(max(__double2hiint(r2), 0x39700000), __double2loint(r2));
+    return c * tps_half_log(c, tps_tab);
+  }
 #if B2_MMA_FAST_SQRT
   if (KERN != B200RBF_KERNEL_TPS) {
     // the seed reads only the high word; clamping it to the smallest normal keeps the seed finite for r2 = 0 (then
@@ -112,6 +158,12 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 <= 4 ? kMmaMinBlocks + 1 : kM
   double* s_nrm = s_wts + kMmaStages * kMmaTileRows;                       // [stages][rows]
   uint64_t* s_full = reinterpret_cast<uint64_t*>(s_nrm + kMmaStages * kMmaTileRows);
   double* s_red = reinterpret_cast<double*>(s_full + kMmaStages);         // 4 x warps
+  // thin-plate spline only: the half-log table (2 KB), 16-byte aligned behind the reduction scratch
+  const double2* s_tps = reinterpret_cast<const double2*>(s_red + 4 * (kMmaThreads / 32) + (kMmaStages & 1));
+  if (KERN == B200RBF_KERNEL_TPS) {
+    double2* dst = const_cast<double2*>(s_tps);
+    for (int i = threadIdx.x; i < kTpsLogEntries; i += kMmaThreads) dst[i] = ma.tps_table[i];
+  }
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gid = lane >> 2, tig = lane & 3;
@@ -260,7 +312,7 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 <= 4 ? kMmaMinBlocks + 1 : kM
           for (int e = 0; e < 2; ++e) {
             const double r2 = acc[i][jb][e];
             min_any |= __double2hiint(r2) <= mnhi[i];
-            sum[i] = fma(mma_phi_from_r2<KERN>(r2), e ? w2.y : w2.x, sum[i]);
+            sum[i] = fma(mma_phi_from_r2<KERN>(r2, s_tps), e ? w2.y : w2.x, sum[i]);
           }
         }
       }
@@ -350,15 +402,15 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 <= 4 ? kMmaMinBlocks + 1 : kM
   }
 }
 
-inline size_t score_mma_smem_bytes(int ds) {
+inline size_t score_mma_smem_bytes(int ds, bool tps = false) {
   return ((size_t)kMmaStages * kMmaTileRows * ds + 2 * (size_t)kMmaStages * kMmaTileRows + kMmaStages +
-          4 * (kMmaThreads / 32)) * 8;
+          4 * (kMmaThreads / 32) + (tps ? 2 * kTpsLogEntries + 1 : 0)) * 8;
 }
 
 template <int K4, int KERN, bool AUG>
 int launch_score_mma_inst(b200rbf_ctx* h, const MmaArgs& ma) {
   auto kern = score_mma_kernel<K4, KERN, AUG>;
-  const size_t smem = score_mma_smem_bytes(ma.ds);
+  const size_t smem = score_mma_smem_bytes(ma.ds, KERN == B200RBF_KERNEL_TPS);
   B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (ma.s.occ_out != nullptr) {
     B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(ma.s.occ_out, kern, kMmaThreads, smem));

@@ -3,6 +3,9 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <vector>
+#ifndef TUNE_KERN
+#define TUNE_KERN 0
+#endif
 #ifndef TUNE_AUG
 #define TUNE_AUG false
 #endif
@@ -41,8 +44,9 @@ int main(int argc, char** argv) {
   a.cand = cand; a.m = m; a.d = d; a.lb = box; a.range = box + pad_dim(d); a.pts = pts; a.coef = coef; a.tailc = tailc;
   a.npad = npad; a.tail = 0; a.dscale = 1.0; a.min_mode = 1; a.fvals = fv; a.dmerit = dm; a.parts = parts; a.nparts = nparts;
   ma.cnorm = nrm; ma.ds = ds; ma.aug = TUNE_AUG;
+  { std::vector<double> ht2(2 * kTpsLogEntries); tps_log_table_host(ht2.data()); double* tt; CK(cudaMalloc(&tt, ht2.size() * 8)); CK(cudaMemcpy(tt, ht2.data(), ht2.size() * 8, cudaMemcpyHostToDevice)); ma.tps_table = reinterpret_cast<const double2*>(tt); }
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-  auto run = [&]() { return launch_score_mma_inst<K4, 0, TUNE_AUG>(&ctx, ma); };
+  auto run = [&]() { return launch_score_mma_inst<K4, TUNE_KERN, TUNE_AUG>(&ctx, ma); };
   for (int i = 0; i < 2; ++i) if (run() != 0) return 1;
   CK(cudaStreamSynchronize(ctx.stream));
   float best = 1e30f;
@@ -50,8 +54,8 @@ int main(int argc, char** argv) {
     CK(cudaEventRecord(e0, ctx.stream)); if (run() != 0) return 1; CK(cudaEventRecord(e1, ctx.stream)); CK(cudaEventSynchronize(e1));
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); best = ms < best ? ms : best;
   }
-  int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, score_mma_kernel<K4, 0, TUNE_AUG>, kMmaThreads, score_mma_smem_bytes(ds));
-  cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, score_mma_kernel<K4, 0, TUNE_AUG>);
+  int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, score_mma_kernel<K4, TUNE_KERN, TUNE_AUG>, kMmaThreads, score_mma_smem_bytes(ds, TUNE_KERN == 1));
+  cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, score_mma_kernel<K4, TUNE_KERN, TUNE_AUG>);
   const double pairs = (double)m * n;
   printf("mma d=%d mb=%d minb=%d jb=%d regs=%d ctas/sm=%d  best %.3f ms  %.4e pairs/s  %.2f TFLOP/s at %d flops/pair\n", d, kMmaMB,
          kMmaMinBlocks, kMmaJB, fa.numRegs, occ, best, pairs / (best * 1e-3), pairs * (3.0 * d + 6) / (best * 1e-3) / 1e12, 3 * d + 6);
