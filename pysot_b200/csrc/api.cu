@@ -25,6 +25,16 @@ int run_lu_debug(b200rbf_ctx* h, double* A_dev, int ld, int N, int rcol0, int nc
 int run_gemm_debug(b200rbf_ctx* h, double* C, int ldc, const double* A, int lda, const double* B, int ldb, int M,
                    int Nc, int K);
 
+// once per handle: the half-log table of the thin-plate-spline epilogues (score_mma.cuh, deriv_tile.cuh)
+int ensure_tps_table(b200rbf_ctx* h) {
+  if (h->tps_table.p != nullptr) return 0;
+  double host[2 * kTpsLogEntries];
+  tps_log_table_host(host);
+  B2_TRY(h->tps_table.reserve(sizeof(host)));
+  B2_CUDA(cudaMemcpy(h->tps_table.p, host, sizeof(host), cudaMemcpyHostToDevice));
+  return 0;
+}
+
 namespace {
 
 enum PtrKind { kPageable = 0, kPinned = 1, kDevice = 2 };
@@ -204,12 +214,7 @@ int launch_score_mma(b200rbf_ctx* h, const ScoreArgs& a) {
   ma.aug = M.aug;
   ma.tps_table = nullptr;
   if (M.kernel == B200RBF_KERNEL_TPS) {
-    if (h->tps_table.p == nullptr) {  // once per handle: the half-log table of the thin-plate-spline epilogue
-      double host[2 * kTpsLogEntries];
-      tps_log_table_host(host);
-      B2_TRY(h->tps_table.reserve(sizeof(host)));
-      B2_CUDA(cudaMemcpy(h->tps_table.p, host, sizeof(host), cudaMemcpyHostToDevice));
-    }
+    B2_TRY(ensure_tps_table(h));
     ma.tps_table = h->tps_table.as<double2>();
   }
   ma.s.pts = M.aug ? M.centers_m.as<double>() : M.centers_x.as<double>();

@@ -8,6 +8,7 @@
 #include "deriv_tile.cuh"
 
 namespace b200rbf {
+int ensure_tps_table(b200rbf_ctx* h);  // api.cu
 namespace {
 
 constexpr int kDerivThreads = 256;
@@ -106,6 +107,11 @@ int launch_deriv(b200rbf_ctx* h, const double* x, long long m, const double* lb,
     a.x = x; a.m = m; a.d = M.d; a.lb = lb; a.range = range;
     a.pts = M.centers_x.as<double>(); a.coef = M.coef.as<double>(); a.tailc = M.tailc.as<double>();
     a.ds = M.ds; a.npad = M.npad; a.tail = M.tail; a.out = out;
+    a.tps_table = nullptr;
+    if (M.kernel == B200RBF_KERNEL_TPS) {
+      B2_TRY(ensure_tps_table(h));
+      a.tps_table = h->tps_table.as<double2>();
+    }
     const int k4 = (M.d + 3) / 4;
     switch ((k4 - 1) / 4) {
       case 0: return launch_deriv_tile_group0(h, a, k4, M.kernel);

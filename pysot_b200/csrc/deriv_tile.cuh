@@ -7,7 +7,7 @@
 // operations per pair.  deriv_kernels.cu keeps the slab-parallel kernel for small query counts, where a thread per
 // query cannot fill the GPU.
 #pragma once
-#include "score_kernels.cuh"
+#include "score_mma.cuh"
 
 namespace b200rbf {
 
@@ -26,16 +26,33 @@ struct DerivTileArgs {
   const double* tailc;  // ntail
   int ds, npad, tail;
   double* out;          // m x d
+  const double2* tps_table;  // half-log table (score_mma.cuh), thin-plate spline only
 };
 
+// s = phi'(r) c / r from r^2 (rbf.py:212 with r clamped to eps, rbf.py:201), without a division and -- for the
+// thin-plate spline -- without a square root:
+//   cubic  (cubic_kernel.py:37)   3 r^2 c / r = 3 c sqrt(r2)                 Newton-corrected rsqrt seed (score_mma.cuh)
+//   TPS    (tps_kernel.py:41-42)  r (1 + 2 log r) c / r = c (1 + 2 * 0.5 log r2)    table-driven half-log
+//   linear (linear_kernel.py:40)  c / r = c rsqrt(max(r2, eps^2))            two Newton steps on the hardware seed
+// Below the clamp the cubic value differs from the reference's by < 1e-15 |c| and multiplies (u - c) < eps: invisible.
 template <int KERN>
-__device__ __forceinline__ double dphi_c_over_r(double r, double c) {
-  // kernels/cubic_kernel.py:37 3 r^2 ; tps_kernel.py:41-42 r (1 + 2 log r) ; linear_kernel.py:40 1 ; rbf.py:212
-  double dp;
-  if (KERN == B200RBF_KERNEL_CUBIC) dp = __dmul_rn(3.0, __dmul_rn(r, r));
-  else if (KERN == B200RBF_KERNEL_TPS) dp = __dmul_rn(r, __dadd_rn(1.0, __dmul_rn(2.0, log(r))));
-  else dp = 1.0;
-  return __ddiv_rn(__dmul_rn(dp, c), r);
+__device__ __forceinline__ double dphi_c_over_r_from_r2(double r2, double c, const double2* __restrict__ tps_tab) {
+  if (KERN == B200RBF_KERNEL_CUBIC) {
+    return (3.0 * c) * mma_phi_from_r2<B200RBF_KERNEL_LINEAR>(r2, nullptr);  // sqrt(r2), exact 0 at r2 = 0
+  } else if (KERN == B200RBF_KERNEL_TPS) {
+    const double cl = __hiloint2double(max(__double2hiint(r2), 0x39700000), __double2loint(r2));  // >= eps^2 = 2^-104
+    return fma(2.0 * c, tps_half_log(cl, tps_tab), c);
+  } else {
+    const double x = fmax(r2, 4.930380657631323783823303533017413935457e-32);  // eps^2
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const double g = x * y;
+      y = fma(y, fma(-g, 0.5 * y, 0.5), y);  // y <- y + y (1 - x y^2) / 2
+    }
+    return c * y;
+  }
 }
 
 template <int K4, int KERN>
@@ -47,6 +64,9 @@ __global__ void __launch_bounds__(kDtThreads, 2) deriv_tile_kernel(DerivTileArgs
   double* s_wts = s_pts + (size_t)kDtStages * kDtTileRows * ds;          // [stages][rows]
   uint64_t* s_full = reinterpret_cast<uint64_t*>(s_wts + kDtStages * kDtTileRows);
   double* s_g = reinterpret_cast<double*>(s_full + kDtStages);          // [DP][threads]
+  const double2* s_tps = reinterpret_cast<const double2*>(s_g + (size_t)DP * kDtThreads);  // TPS: half-log table
+  if (KERN == B200RBF_KERNEL_TPS)
+    for (int i = threadIdx.x; i < kTpsLogEntries; i += kDtThreads) const_cast<double2*>(s_tps)[i] = a.tps_table[i];
 
   const int tid = threadIdx.x;
   const long long row = (long long)blockIdx.x * kDtThreads + tid;
@@ -79,8 +99,6 @@ __global__ void __launch_bounds__(kDtThreads, 2) deriv_tile_kernel(DerivTileArgs
       s_g[k * kDtThreads + tid] = 0.0;
     }
   }
-  const double eps = 2.220446049250313e-16;
-
   for (int t = 0; t < ntiles; ++t) {
     const int s = t % kDtStages;
     const int rows = min(kDtTileRows, a.npad - t * kDtTileRows);  // multiple of 16
@@ -103,9 +121,7 @@ __global__ void __launch_bounds__(kDtThreads, 2) deriv_tile_kernel(DerivTileArgs
       double fac[4];
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
-        double r = sqrt(acc[jj]);
-        if (r < eps) r = eps;  // rbf.py:201
-        fac[jj] = dphi_c_over_r<KERN>(r, tw[j0 + jj]);  // pad rows carry weight 0
+        fac[jj] = dphi_c_over_r_from_r2<KERN>(acc[jj], tw[j0 + jj], s_tps);  // pad rows carry weight 0
       }
 #pragma unroll
       for (int k = 0; k < DP; k += 2) {
@@ -136,7 +152,7 @@ template <int K4, int KERN>
 int launch_deriv_tile_inst(b200rbf_ctx* h, const DerivTileArgs& a) {
   auto kern = deriv_tile_kernel<K4, KERN>;
   const size_t smem = ((size_t)kDtStages * kDtTileRows * a.ds + kDtStages * kDtTileRows + kDtStages +
-                       (size_t)4 * K4 * kDtThreads) * 8;
+                       (size_t)4 * K4 * kDtThreads + (KERN == B200RBF_KERNEL_TPS ? 2 * kTpsLogEntries : 0)) * 8;
   B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)((a.m + kDtThreads - 1) / kDtThreads), kDtThreads, smem, h->stream>>>(a);
   h->launches++;
