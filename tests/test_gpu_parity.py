@@ -446,6 +446,34 @@ def test_mma_and_direct_kernels_agree_on_clustered_points(pb, orc):
         assert np.array_equal(idx, tr["picked"]), mode
 
 
+@pytest.mark.parametrize("kernel,tail", [("cubic", "linear"), ("tps", "linear"), ("linear", "constant")])
+@pytest.mark.parametrize("d", [5, 6, 7, 8, 49, 52])
+def test_score_and_gradient_kernels_over_dimension_classes(pb, orc, kernel, tail, d):
+    """d mod 4 decides the DMMA kernel's variant (norms inside the MMA for 1, 2; separate for 3, 0); each kernel has its
+    own epilogue (rsqrt-based square root, table-driven half-log) and its own gradient scalar.  Same coefficients on
+    both sides, 5000 candidates / queries (tile kernels), against the oracle."""
+    rng = np.random.default_rng(100 + d)
+    n, m = 333, 5000
+    lb, ub = -1.0 - rng.random(d), 1.0 + rng.random(d)
+    X = lb + (ub - lb) * rng.random((n, d))
+    fX = np.sin(X.sum(1))[:, None]
+    o = orc.OracleRBF(d, lb, ub, kernel, tail)
+    o.add_points(X, fX)
+    o.fit()
+    s = make_gpu(pb, d, lb, ub, kernel, tail)
+    s.add_points(X, fX)
+    s.set_coefficients(o.c)
+    q = lb + (ub - lb) * rng.random((m, d))
+    q[:20] = X[:20]  # coincident points: r = 0 in both the value and the gradient path
+    assert relmax(s.predict(q), o.predict(q)) < 1e-12
+    assert relmax(s.predict_deriv(q), o.predict_deriv(q)) < 1e-11
+    tr = {}
+    orc.weighted_distance_merit(3, o, X, fX, q.copy(), [0.3, 0.5, 0.95], None, 1e-3, trace=tr)
+    idx, _, fv, dm, _ = pb.merit_select_indices(3, s, X, q, [0.3, 0.5, 0.95], None, want_scores=True)
+    assert relmax(fv, tr["fvals_raw"].ravel()) < 1e-12 and relmax(dm, tr["dmerit0"].ravel()) < 1e-12
+    assert np.all(dm[:20] == 0.0) and np.array_equal(idx, tr["picked"])
+
+
 @pytest.mark.parametrize("kernel,d,n", [("cubic", 3, 150), ("tps", 10, 1000), ("cubic", 30, 1500), ("tps", 2, 700)])
 def test_cholesky_fit_matches_lu_and_oracle(pb, orc, kernel, d, n):
     """The null-space Cholesky solver (fit_chol.cu) against the pivoted LU and the reference's dgetrf path."""
