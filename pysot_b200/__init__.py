@@ -12,6 +12,7 @@ from .interface import (  # noqa: F401
     HAVE_PYSOT, ConstantTail, CubicKernel, Kernel, LinearKernel, LinearTail, Surrogate, Tail, TPSKernel, identity,
     median_capping,
 )
+from .pareto import nd_sorting  # noqa: F401
 from .rbf import GpuRBFInterpolant  # noqa: F401
 from .candidates import (  # noqa: F401
     candidate_dycors, candidate_srbf, candidate_uniform, generate_dycors, generate_on_device, generate_srbf,

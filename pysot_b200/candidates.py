@@ -16,6 +16,7 @@ DYCORSStrategy and SOPStrategy use these functions unchanged.
 import numpy as np
 import scipy.stats as stats
 
+from .pareto import nd_sorting
 from .rbf import GpuRBFInterpolant
 
 
@@ -304,12 +305,16 @@ _BINDINGS = [
     ("pySOT.auxiliary_problems.candidate_dycors", "candidate_dycors"),
     ("pySOT.auxiliary_problems.candidate_uniform", "weighted_distance_merit"),
     ("pySOT.auxiliary_problems.candidate_uniform", "candidate_uniform"),
+    # host side of SOPStrategy: numpy non-dominated sorting with the reference's exact output (pareto.py)
+    ("pySOT.strategy.sop_strategy", "nd_sorting"),
+    ("pySOT.utils", "nd_sorting"),
 ]
 _saved = {}
 
 
 def install():
-    """Rebind pySOT's candidate functions to the GPU versions.  Returns the list of names rebound."""
+    """Rebind pySOT's candidate functions to the GPU versions (and SOP's ``nd_sorting`` to the numpy version with
+    identical output).  Returns the list of names rebound."""
     import importlib
 
     mine = globals()
