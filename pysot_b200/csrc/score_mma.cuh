@@ -34,8 +34,10 @@ constexpr int kMmaMB = B2_MMA_MB;          // m8 candidate blocks per warp (A fr
 #define B2_MMA_JB 4
 #endif
 constexpr int kMmaJB = B2_MMA_JB;          // n8 center blocks per step (8 * JB centers = one tile)
-constexpr int kMmaMinBlocks = B2_MMA_MINB; // CTAs per SM the register budget is capped for (+1 when d <= 16);
-                                           // tools/k2x_tune.cu sweep: 2 x 4 beats 2 x 3 by 6 %, 4 x 2 by 16 % at d = 50
+constexpr int kMmaMinBlocks = B2_MMA_MINB; // CTAs per SM the register budget is capped for (one less when d >= 45).
+                                           // tools/k2x_tune.cu with the current epilogue (ms per 2^20 x 20000, 3 / 4 / 5
+                                           // CTAs): d = 10 - / 28.9 / 30.5, d = 20 42.2 / 41.8 / -, d = 30 52.4 / 52.7 / -,
+                                           // d = 50 76.6 / 77.6 / 84.8 (3 CTAs: 168 registers, no spills)
 constexpr int kMmaTileRows = 8 * kMmaJB;   // center rows per tile
 static_assert(32 % kMmaTileRows == 0, "pad_rows() pads the center rows to multiples of 32: tiles must divide that");
 #ifndef B2_MMA_STAGES
@@ -149,7 +151,7 @@ static __device__ __noinline__ double mma_exact_r2(const double* __restrict__ sr
 // A row = (-2 u, |u|^2, 1), B row = (c, 1, |c|^2) -- so the MMA accumulates r^2 itself and pass 1 needs no FP64
 // instruction at all; the near test then compares against 2^-10 max(|u|^2, |c|^2) (integer max of the high words).
 template <int K4, int KERN, bool AUG>
-__global__ void __launch_bounds__(kMmaThreads, (K4 <= 4 ? kMmaMinBlocks + 1 : kMmaMinBlocks)) score_mma_kernel(MmaArgs ma) {
+__global__ void __launch_bounds__(kMmaThreads, (K4 >= 12 ? kMmaMinBlocks - 1 : kMmaMinBlocks)) score_mma_kernel(MmaArgs ma) {
   const ScoreArgs& a = ma.s;
   const int ds = ma.ds;
   extern __shared__ __align__(128) unsigned char smem_raw[];
