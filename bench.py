@@ -346,7 +346,7 @@ def run_native(args, rank, world, local_rank):
         "flops_per_pair": FLOPS_PER_PAIR,
         "note": "achieved counts SURVEY 8(d)'s ALGORITHMIC 3d+6 flops per pair (direct differences); the kernel executes "
                 "2*52 (DMMA) + 7 on the shared FP64 FMA/DMMA datapath, so a fraction above 1 is arithmetic savings, not a faster pipe "
-                "(ncu: that datapath is 86 % busy)",
+                "(ncu: that datapath is 87.5 % busy)",
         "launch_ms": k_ms, "share_of_step": k_ms * args.steps / dev_ms,
         "dmma_peak_tflops": peaks["dmma_tflops"], "traffic": traffic,
         "hbm": {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (k_ms * 1e-3) / 1e9, "peak_gbs": mp["hbm_gbs"],
