@@ -474,7 +474,12 @@ def test_score_and_gradient_kernels_over_dimension_classes(pb, orc, kernel, tail
     assert np.all(dm[:20] == 0.0) and np.array_equal(idx, tr["picked"])
 
 
-@pytest.mark.parametrize("kernel,d,n", [("cubic", 3, 150), ("tps", 10, 1000), ("cubic", 30, 1500), ("tps", 2, 700)])
+# n around the 32 / 128 / 512 blocking of the two-level Cholesky (padding rows, one-block case, last partial panel of
+# an outer panel, first column right of an outer panel)
+@pytest.mark.parametrize("kernel,d,n", [("cubic", 3, 150), ("tps", 10, 1000), ("cubic", 30, 1500), ("tps", 2, 700),
+                                        ("cubic", 4, 128), ("tps", 4, 129), ("cubic", 5, 161), ("tps", 3, 256),
+                                        ("cubic", 3, 257), ("tps", 6, 511), ("cubic", 6, 513), ("tps", 5, 640),
+                                        ("cubic", 2, 1025)])
 def test_cholesky_fit_matches_lu_and_oracle(pb, orc, kernel, d, n):
     """The null-space Cholesky solver (fit_chol.cu) against the pivoted LU and the reference's dgetrf path."""
     from pysot_b200 import _lib
