@@ -264,7 +264,9 @@ def run_native(args, rank, world, local_rank):
     rbf._fit()  # every rank fits its own replica (the fit does not shard: "replicas only")
     fit50 = {"n": N_CENTERS, "d": D, "kernel": "cubic", "solver": rbf.handle.last_fit_method,
              "seconds_device": rbf.fit_seconds,
-             "seconds_host_to_host": time.perf_counter() - t0}
+             "seconds_host_to_host": time.perf_counter() - t0,
+             "note": "cold: the first fit of the process, it allocates the 3.4 GB workspace inside the timed region; "
+                     "the warm figures are in `fit`"}
     h = rbf.handle
     Xdist = np.vstack((X, Xpend))
 
