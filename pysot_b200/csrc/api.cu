@@ -426,7 +426,7 @@ int b200rbf_destroy(b200rbf_handle h) {
   cudaStreamSynchronize(h->stream);
   cudaStreamSynchronize(h->copy_stream);
   Model& M = h->model;
-  M.centers.release(); M.centersT.release(); M.coef.release(); M.tailc.release();
+  M.centers.release(); M.coef.release(); M.tailc.release();
   M.centers_x.release(); M.centers_m.release(); M.cnorm.release();
   ScoreState& S = h->score;
   S.cand_own.release(); S.fvals.release(); S.dmerit.release(); S.parts.release(); S.pair_parts.release();

@@ -129,10 +129,8 @@ struct Model {
   int n = 0, d = 0, dpad = 0, npad = 0, kernel = 0, tail = 0, ntail = 0;
   bool loaded = false;
   DevBuf centers;   // npad x dpad unit-box coordinates (pad rows = last row, pad dims = 0)
-  DevBuf centersT;  // dpad x npadT  transposed copy for predict_deriv
   DevBuf coef;      // npad RBF weights (pad = 0)
   DevBuf tailc;     // ntail tail coefficients (lambda_0, lambda_1..d)
-  int npadT = 0;
   // operands of the DMMA score kernel (score_mma.cuh): centers with row stride ds and their squared norms
   DevBuf centers_x, cnorm;
   DevBuf centers_m;         // the same with (1, |c|^2) in slots d, d + 1 when `aug`
