@@ -253,13 +253,47 @@ def generate_uniform(opt_prob, X, fX, subset=None, num_cand=None):
     return _round_vars(cand, opt_prob.int_var, opt_prob.lb, opt_prob.ub)
 
 
+class _Prefit:
+    """Runs the surrogate's lazy refit on a worker thread while the caller draws candidates on the host: the fit is one
+    ctypes call (the GIL is released for its duration) and the host generators are numpy / scipy work of comparable
+    length, so in host-generator mode the fit disappears behind the random numbers.  Nothing else touches the handle
+    until ``join()``; an exception raised by the fit is re-raised there.  The RNG is only ever used by the caller's
+    thread, so seeded runs are unaffected."""
+
+    def __init__(self, surrogate):
+        self._exc = None
+        self._thread = None
+        if isinstance(surrogate, GpuRBFInterpolant) and not surrogate.updated and surrogate.num_pts >= surrogate.ntail:
+            import threading
+
+            self._thread = threading.Thread(target=self._run, args=(surrogate,), daemon=True)
+            self._thread.start()
+
+    def _run(self, surrogate):
+        try:
+            surrogate._fit()
+        except BaseException as e:  # noqa: BLE001 -- handed to the caller's thread
+            self._exc = e
+
+    def join(self):
+        if self._thread is not None:
+            self._thread.join()
+            self._thread = None
+            if self._exc is not None:
+                raise self._exc
+
+
 def candidate_srbf(num_pts, opt_prob, surrogate, X, fX, weights, Xpend=None, sampling_radius=0.2, subset=None,
                    dtol=1e-3, num_cand=None):
     """candidate_srbf.py:60-121."""
     if _GENERATOR["mode"] == "device":
         cand = generate_on_device("srbf", opt_prob, surrogate, X, fX, 1.0, sampling_radius, subset, num_cand)
     else:
-        cand = generate_srbf(opt_prob, X, fX, sampling_radius, subset, num_cand)
+        pre = _Prefit(surrogate)
+        try:
+            cand = generate_srbf(opt_prob, X, fX, sampling_radius, subset, num_cand)
+        finally:
+            pre.join()
     return weighted_distance_merit(num_pts=num_pts, surrogate=surrogate, X=X, fX=fX, Xpend=Xpend, cand=cand,
                                    dtol=dtol, weights=weights)
 
@@ -271,7 +305,11 @@ def candidate_dycors(num_pts, opt_prob, surrogate, X, fX, weights, prob_perturb,
         cand = generate_on_device("dycors", opt_prob, surrogate, X, fX, prob_perturb, sampling_radius, subset, num_cand,
                                   xbest)
     else:
-        cand = generate_dycors(opt_prob, X, fX, prob_perturb, sampling_radius, subset, num_cand, xbest)
+        pre = _Prefit(surrogate)
+        try:
+            cand = generate_dycors(opt_prob, X, fX, prob_perturb, sampling_radius, subset, num_cand, xbest)
+        finally:
+            pre.join()
     return weighted_distance_merit(num_pts=num_pts, surrogate=surrogate, X=X, fX=fX, Xpend=Xpend, cand=cand,
                                    dtol=dtol, weights=weights)
 
@@ -282,7 +320,11 @@ def candidate_uniform(num_pts, opt_prob, surrogate, X, fX, weights, Xpend=None, 
     if _GENERATOR["mode"] == "device":
         cand = generate_on_device("uniform", opt_prob, surrogate, X, fX, 1.0, 0.2, subset, num_cand)
     else:
-        cand = generate_uniform(opt_prob, X, fX, subset, num_cand)
+        pre = _Prefit(surrogate)
+        try:
+            cand = generate_uniform(opt_prob, X, fX, subset, num_cand)
+        finally:
+            pre.join()
     return weighted_distance_merit(num_pts=num_pts, surrogate=surrogate, X=X, fX=fX, Xpend=Xpend, cand=cand,
                                    dtol=dtol, weights=weights)
 
