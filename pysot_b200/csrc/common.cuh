@@ -117,7 +117,10 @@ constexpr int kJT = B2_JT;                      // centers processed together pe
 constexpr int kGenMaxDim = 192;                 // largest padded dimension of the shared-memory (generic) score kernel
 
 inline int pad_dim(int d) { return (d + 1) & ~1; }                       // even: rows are multiples of 16 B
-inline int pad_rows(int n) { return (n + 31) & ~31; }                    // multiples of 32 (duplicates of last row)
+#ifndef B2_PAD_ROWS
+#define B2_PAD_ROWS 32  // center rows are padded to multiples of this (duplicates of the last row); tuning builds may raise it
+#endif
+inline int pad_rows(int n) { return (n + B2_PAD_ROWS - 1) / B2_PAD_ROWS * B2_PAD_ROWS; }
 inline int mma_stride(int d) {                                            // center row stride of the DMMA kernel:
   int s = (d + 3) & ~3;                                                   // >= 4 ceil(d/4), == 4 (mod 16) doubles so the
   while ((s & 15) != 4) s += 4;                                           // B-fragment LDS.64 are bank-conflict free

@@ -39,7 +39,7 @@ constexpr int kMmaMinBlocks = B2_MMA_MINB; // CTAs per SM the register budget is
                                            // CTAs): d = 10 - / 28.9 / 30.5, d = 20 42.2 / 41.8 / -, d = 30 52.4 / 52.7 / -,
                                            // d = 50 76.6 / 77.6 / 84.8 (3 CTAs: 168 registers, no spills)
 constexpr int kMmaTileRows = 8 * kMmaJB;   // center rows per tile
-static_assert(32 % kMmaTileRows == 0, "pad_rows() pads the center rows to multiples of 32: tiles must divide that");
+static_assert(B2_PAD_ROWS % kMmaTileRows == 0, "pad_rows() pads the center rows to multiples of B2_PAD_ROWS: tiles must divide that");
 #ifndef B2_MMA_STAGES
 #define B2_MMA_STAGES 3
 #endif
