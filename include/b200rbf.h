@@ -56,8 +56,9 @@ enum {
   /* DMMA GEMM variant: 2 or 3 = cp.async stages at BK 16, 4 = 2 stages at BK 32; 0 = auto (4; 2 under LU look-ahead) */
   B200RBF_OPT_GEMM_STAGES = 5,
   /* 1 (default): surrogate values use the norm expansion |u|^2 + |c|^2 - 2 u.c with the dot products on the FP64
-   *    tensor path and a direct recomputation of near pairs (score_mma.cuh; ~1.6x fewer FP64 cycles at d = 50,
-   *    relative error of r^2 <= ~1e-12).  0: direct differences everywhere.  Ignored when EXACT_DIST is set.     */
+   *    tensor path and a direct recomputation of near pairs (score_mma.cuh; 1.9x the rate of the direct kernel at
+   *    d = 50, relative error of r^2 <= ~1e-12; square roots / logarithms built from the hardware seeds, <= 1 ulp).
+   *    0: direct differences everywhere.  Ignored when EXACT_DIST is set.                                        */
   B200RBF_OPT_MMA_DIST = 6,
   /* solver of b200rbf_fit: 0 (default) auto = null-space Cholesky for cubic / TPS + linear tail with n >= 128, pivoted
    *    LU otherwise and whenever the Cholesky reports a non-positive pivot; 1 = always LU; 2 = Cholesky or error       */
