@@ -73,11 +73,34 @@ def merit_select_indices(num_pts, surrogate, X, cand, weights, Xpend=None, dtol=
     # distance serves both metrics.  extra_points (surrogate_strategy.py:243-247) break the aliasing.
     alias = X.shape == surrogate.X.shape and np.array_equal(X, surrogate.X)
     h = surrogate.handle
-    fv, dm, st = h.score(cand, surrogate.lb, surrogate.ub, Xdist, alias, want_scores=want_scores, m=cand.shape[0])
-    idx, merit = h.select(weights, num_pts, dtol)
+    with _torch_stream(h, cand):
+        fv, dm, st = h.score(cand, surrogate.lb, surrogate.ub, Xdist, alias, want_scores=want_scores, m=cand.shape[0])
+        idx, merit = h.select(weights, num_pts, dtol)
     if want_scores:
         return idx, merit, fv, dm, st
     return idx, merit
+
+
+class _torch_stream:
+    """While a CUDA tensor is handed to the library, its kernels are enqueued on torch's current stream for that
+    device: whatever produced the tensor (torch ops, ``generate_on_device``) is ordered before them, and whatever
+    consumes the results afterwards (``.cpu()``, indexing) after them.  With a host array the handle keeps its own
+    stream."""
+
+    def __init__(self, handle, tensor):
+        self._h = handle if _is_cuda_tensor(tensor) else None
+        self._t = tensor
+
+    def __enter__(self):
+        if self._h is not None:
+            import torch
+
+            self._h.set_stream(torch.cuda.current_stream(self._t.device).cuda_stream)
+
+    def __exit__(self, *exc):
+        if self._h is not None:
+            self._h.set_stream(None)
+        return False
 
 
 # ------------------------------------------------------------------------------------------ where candidates are drawn
@@ -105,8 +128,9 @@ def generate_on_device(kind, opt_prob, surrogate, X, fX, prob_perturb=1.0, sampl
         seed = (_GENERATOR["seed"] * 0x9E3779B97F4A7C15 + _GENERATOR["calls"] * 0xD1B54A32D192ED03 + 1) & 0xFFFFFFFFFFFFFFFF
         _GENERATOR["calls"] += 1
     cand = torch.empty((int(num_cand), opt_prob.dim), dtype=torch.float64, device=torch.device("cuda", surrogate._device))
-    surrogate.handle.generate(kind, int(num_cand), xbest, opt_prob.lb, opt_prob.ub, sigma, prob_perturb,
-                              np.asarray(subset, dtype=np.int32), opt_prob.int_var, seed, cand)
+    with _torch_stream(surrogate.handle, cand):  # ordered with the torch operations on the tensor, before and after
+        surrogate.handle.generate(kind, int(num_cand), xbest, opt_prob.lb, opt_prob.ub, sigma, prob_perturb,
+                                  np.asarray(subset, dtype=np.int32), opt_prob.int_var, seed, cand)
     return cand
 
 
