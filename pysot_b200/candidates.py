@@ -41,14 +41,25 @@ def weighted_distance_merit(num_pts, surrogate, X, fX, cand, weights, Xpend=None
     float64 numpy array of rows copied from ``cand``.
     """
     if not isinstance(surrogate, GpuRBFInterpolant):
-        raise TypeError("pysot_b200.weighted_distance_merit needs a GpuRBFInterpolant (there is no CPU fallback); got %r"
-                        % type(surrogate).__name__)
+        return _reference_or_raise("weighted_distance_merit", surrogate, num_pts=num_pts, surrogate=surrogate, X=X, fX=fX,
+                                   cand=cand, weights=weights, Xpend=Xpend, dtol=dtol)
     idx = merit_select_indices(num_pts, surrogate, X, cand, weights, Xpend, dtol)[0]
     if _is_cuda_tensor(cand):
         import torch
 
         return cand[torch.as_tensor(idx, device=cand.device)].cpu().numpy()
     return np.asarray(cand, dtype=np.float64)[idx, :].copy()
+
+
+def _reference_or_raise(name, surrogate_obj, **kw):
+    """A surrogate that is not a GpuRBFInterpolant (pySOT's GP / MARS / polynomial / stock RBF surrogates) keeps working
+    after install(): the call goes to the reference function install() replaced.  Without install() there is nothing to
+    delegate to, and the GPU path itself never falls back to the CPU."""
+    for (modname, attr), fn in _saved.items():
+        if attr == name:
+            return fn(**kw)
+    raise TypeError("pysot_b200.%s needs a GpuRBFInterpolant (there is no CPU fallback); got %r"
+                    % (name, type(surrogate_obj).__name__))
 
 
 def merit_select_indices(num_pts, surrogate, X, cand, weights, Xpend=None, dtol=1e-3, want_scores=False):
@@ -310,6 +321,10 @@ class _Prefit:
 def candidate_srbf(num_pts, opt_prob, surrogate, X, fX, weights, Xpend=None, sampling_radius=0.2, subset=None,
                    dtol=1e-3, num_cand=None):
     """candidate_srbf.py:60-121."""
+    if not isinstance(surrogate, GpuRBFInterpolant):
+        return _reference_or_raise("candidate_srbf", surrogate, num_pts=num_pts, opt_prob=opt_prob, surrogate=surrogate, X=X,
+                                   fX=fX, weights=weights, Xpend=Xpend, sampling_radius=sampling_radius, subset=subset,
+                                   dtol=dtol, num_cand=num_cand)
     if _GENERATOR["mode"] == "device":
         cand = generate_on_device("srbf", opt_prob, surrogate, X, fX, 1.0, sampling_radius, subset, num_cand)
     else:
@@ -325,6 +340,10 @@ def candidate_srbf(num_pts, opt_prob, surrogate, X, fX, weights, Xpend=None, sam
 def candidate_dycors(num_pts, opt_prob, surrogate, X, fX, weights, prob_perturb, Xpend=None, sampling_radius=0.2,
                      subset=None, dtol=1e-3, num_cand=None, xbest=None):
     """candidate_dycors.py:8-94."""
+    if not isinstance(surrogate, GpuRBFInterpolant):
+        return _reference_or_raise("candidate_dycors", surrogate, num_pts=num_pts, opt_prob=opt_prob, surrogate=surrogate,
+                                   X=X, fX=fX, weights=weights, prob_perturb=prob_perturb, Xpend=Xpend,
+                                   sampling_radius=sampling_radius, subset=subset, dtol=dtol, num_cand=num_cand, xbest=xbest)
     if _GENERATOR["mode"] == "device":
         cand = generate_on_device("dycors", opt_prob, surrogate, X, fX, prob_perturb, sampling_radius, subset, num_cand,
                                   xbest)
@@ -341,6 +360,9 @@ def candidate_dycors(num_pts, opt_prob, surrogate, X, fX, weights, prob_perturb,
 def candidate_uniform(num_pts, opt_prob, surrogate, X, fX, weights, Xpend=None, subset=None, dtol=1e-3,
                       num_cand=None):
     """candidate_uniform.py:7-53."""
+    if not isinstance(surrogate, GpuRBFInterpolant):
+        return _reference_or_raise("candidate_uniform", surrogate, num_pts=num_pts, opt_prob=opt_prob, surrogate=surrogate,
+                                   X=X, fX=fX, weights=weights, Xpend=Xpend, subset=subset, dtol=dtol, num_cand=num_cand)
     if _GENERATOR["mode"] == "device":
         cand = generate_on_device("uniform", opt_prob, surrogate, X, fX, 1.0, 0.2, subset, num_cand)
     else:

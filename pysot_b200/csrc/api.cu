@@ -400,22 +400,29 @@ int b200rbf_create(int device, b200rbf_handle* out) {
   B2_CHECK(h != nullptr, B200RBF_ENOMEM, "out of host memory");
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
-  B2_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
-  B2_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-  h->stream = h->own_stream;
-  for (int i = 0; i < 2; ++i) B2_CUDA(cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming));
-  B2_CUDA(cudaEventCreate(&h->ev_t0));
-  B2_CUDA(cudaEventCreate(&h->ev_t1));
-  {
+  h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  auto init = [&]() -> int {
+    B2_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    B2_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    for (int i = 0; i < 2; ++i) B2_CUDA(cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming));
+    B2_CUDA(cudaEventCreate(&h->ev_t0));
+    B2_CUDA(cudaEventCreate(&h->ev_t1));
     int lo = 0, hi = 0;  // numerically lower = higher priority
     B2_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     B2_CUDA(cudaStreamCreateWithPriority(&h->la_stream, cudaStreamNonBlocking, hi));
     B2_CUDA(cudaEventCreateWithFlags(&h->ev_la1, cudaEventDisableTiming));
     B2_CUDA(cudaEventCreateWithFlags(&h->ev_la2, cudaEventDisableTiming));
+    B2_CUDA(cudaEventCreate(&h->ev_s0));
+    B2_CUDA(cudaEventCreate(&h->ev_s1));
+    B2_CUDA(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
+    return 0;
+  };
+  const int rc = init();
+  if (rc != 0) {  // a failure half way: release what exists (destroy tolerates the null members)
+    b200rbf_destroy(h);
+    return rc;
   }
-  B2_CUDA(cudaEventCreate(&h->ev_s0));
-  B2_CUDA(cudaEventCreate(&h->ev_s1));
-  B2_CUDA(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
   *out = h;
   return 0;
 }
@@ -423,8 +430,8 @@ int b200rbf_create(int device, b200rbf_handle* out) {
 int b200rbf_destroy(b200rbf_handle h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
-  cudaStreamSynchronize(h->stream);
-  cudaStreamSynchronize(h->copy_stream);
+  if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+  if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
   Model& M = h->model;
   M.centers.release(); M.coef.release(); M.tailc.release();
   M.centers_x.release(); M.centers_m.release(); M.cnorm.release();
@@ -436,14 +443,16 @@ int b200rbf_destroy(b200rbf_handle h) {
   h->tmp_in.release(); h->tmp_out.release(); h->tmp_box.release(); h->gen_buf.release(); h->gen_pin.release();
   h->tps_table.release();
   h->stage[0].release(); h->stage[1].release(); h->pin_small.release();
-  for (int i = 0; i < 2; ++i) cudaEventDestroy(h->ev_copy[i]);
-  cudaEventDestroy(h->ev_t0); cudaEventDestroy(h->ev_t1); cudaEventDestroy(h->ev_done);
-  cudaEventDestroy(h->ev_s0); cudaEventDestroy(h->ev_s1);
-  cudaEventDestroy(h->ev_la1); cudaEventDestroy(h->ev_la2);
-  cudaStreamSynchronize(h->la_stream);
-  cudaStreamDestroy(h->la_stream);
-  cudaStreamDestroy(h->own_stream);
-  cudaStreamDestroy(h->copy_stream);
+  cudaEvent_t evs[] = {h->ev_copy[0], h->ev_copy[1], h->ev_t0, h->ev_t1, h->ev_done, h->ev_s0, h->ev_s1, h->ev_la1, h->ev_la2};
+  for (cudaEvent_t e : evs)
+    if (e) cudaEventDestroy(e);
+  cudaStream_t streams[] = {h->la_stream, h->own_stream, h->copy_stream};
+  for (cudaStream_t st : streams)
+    if (st) {
+      cudaStreamSynchronize(st);
+      cudaStreamDestroy(st);
+    }
+  cudaGetLastError();
   delete h;
   return 0;
 }
@@ -522,9 +531,12 @@ int b200rbf_fit(b200rbf_handle h, const double* Xu, const double* rhs, int n, in
   B2_CUDA(cudaEventRecord(h->ev_t0, h->stream));
   // Null-space Cholesky (fit_chol.cu) where it applies: conditionally positive definite kernel + linear tail, and a
   // system large enough for the factorisation to matter.  Anything else, and any Cholesky failure, takes the pivoted LU.
-  const bool chol_ok = tail == B200RBF_TAIL_LINEAR && kernel != B200RBF_KERNEL_LINEAR && n >= 2 * t + 32 && t <= 256;
+  // its t x t helper kernels keep a (t rounded to 16)^2 matrix in shared memory: t <= 160 within the 227 KB opt-in limit
+  const size_t tp16 = (size_t)((t + 15) & ~15);
+  const bool chol_ok = tail == B200RBF_TAIL_LINEAR && kernel != B200RBF_KERNEL_LINEAR && n >= 2 * t + 32 &&
+                       tp16 * tp16 * sizeof(double) <= (size_t)h->max_smem_optin;
   B2_CHECK(h->fit_method != 2 || chol_ok, B200RBF_EINVAL,
-           "the Cholesky fit needs a cubic / TPS kernel with the linear tail and n >= 2 ntail + 32");
+           "the Cholesky fit needs a cubic / TPS kernel with the linear tail, n >= 2 ntail + 32 and dim <= 159");
   bool done = false;
   if (chol_ok && (h->fit_method == 2 || (h->fit_method == 0 && n >= 128))) {
     B2_TRY(h->fit.piv.reserve(256));
@@ -653,7 +665,8 @@ int b200rbf_score(b200rbf_handle h, const double* cand, long long m, const doubl
   B2_TRY(upload_box(h, lb, ub, M.d, M.dpad, S.box, &iso, &scale));
 
   ScorePlan plan;
-  plan.shared_min = alias_centers && iso;
+  // EXACT_DIST promises cdist's bits in ORIGINAL coordinates: no shortcut through the unit-box distance then
+  plan.shared_min = alias_centers && iso && !h->exact_dist;
   plan.dscale = plan.shared_min ? scale : 1.0;
   const int first = plan.shared_min ? M.n : 0;  // rows of Xdist that still need the original-space pass
   const int extra = ndist - first;

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -33,6 +34,17 @@ void set_error(const char* fmt, ...);
       return (code);                     \
     }                                    \
   } while (0)
+
+// Function attributes (the > 48 KB shared-memory opt-in) are PER DEVICE, and handles on different devices -- or a
+// worker thread running a fit -- may reach the same launch site: one bit per device ordinal, set after the attribute
+// calls succeeded.  Setting an attribute twice is harmless, so a benign race only repeats the call.
+struct DeviceOnce {
+  std::atomic<unsigned long long> mask{0};
+  bool pending(int device) const { return device >= 64 || !((mask.load(std::memory_order_acquire) >> device) & 1ull); }
+  void done(int device) {
+    if (device < 64) mask.fetch_or(1ull << device, std::memory_order_release);
+  }
+};
 
 // ---------------------------------------------------------------- device buffers (grow-only)
 struct DevBuf {
@@ -178,6 +190,7 @@ struct CholWork {
 struct b200rbf_ctx {
   int device = 0;
   int sm_count = 0;
+  int max_smem_optin = 0;  // cudaDevAttrMaxSharedMemoryPerBlockOptin
   cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_t0 = nullptr, ev_t1 = nullptr, ev_done = nullptr;
   cudaEvent_t ev_s0 = nullptr, ev_s1 = nullptr;  // around the fused score kernel(s) of the last b200rbf_score

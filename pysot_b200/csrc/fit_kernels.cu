@@ -568,13 +568,13 @@ __global__ void __launch_bounds__(256) dmix_peak_kernel(double* out, int iters, 
 template <int STAGES, int BK>
 static int gemm_sub_inst(b200rbf_ctx* h, double* C, int ldc, const double* A, int lda, const double* B, int ldb, int M,
                          int Nc, int K, int lower) {
-  static bool attr = false;
+  static DeviceOnce attr;
   constexpr size_t smem = gemm_smem_bytes<BK>(STAGES);
-  if (!attr) {
+  if (attr.pending(h->device)) {
     B2_CUDA(cudaFuncSetAttribute(gemm_sub_kernel<STAGES, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     B2_CUDA(cudaFuncSetAttribute(gemm_sub_kernel<STAGES, BK>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  (int)cudaSharedmemCarveoutMaxShared));
-    attr = true;
+    attr.done(h->device);
   }
   dim3 grid((Nc + kGemmBN - 1) / kGemmBN, (M + kGemmBM - 1) / kGemmBM);
   gemm_sub_kernel<STAGES, BK><<<grid, kGemmThreads, smem, h->stream>>>(C, ldc, A, lda, B, ldb, M, Nc, K, lower);
@@ -640,10 +640,10 @@ int lu_factor_device(b200rbf_ctx* h, double* A, int ld, int N, int rcol0, int nc
 
   int max_smem = 0;
   B2_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  if (attr.pending(h->device)) {
     B2_CUDA(cudaFuncSetAttribute(panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 1024));
-    attr = true;
+    attr.done(h->device);
   }
 
   // factor the panel starting at column j0 on `stream`
@@ -705,7 +705,11 @@ int lu_factor_device(b200rbf_ctx* h, double* A, int ld, int N, int rcol0, int nc
   };
 
   const bool lookahead = h->lu_lookahead && h->la_stream != nullptr;
-  const int saved_stages = h->gemm_stages;
+  struct StagesGuard {  // restores the GEMM variant on every return path, the early error returns included
+    b200rbf_ctx* h;
+    int saved;
+    ~StagesGuard() { h->gemm_stages = saved; }
+  } stages_guard{h, h->gemm_stages};
   if (lookahead && h->gemm_stages_auto) h->gemm_stages = 2;
   B2_TRY(launch_panel(0, h->stream));
   for (int j0 = 0; j0 < N; j0 += NB) {
@@ -739,16 +743,15 @@ int lu_factor_device(b200rbf_ctx* h, double* A, int ld, int N, int rcol0, int nc
       B2_TRY(launch_panel(c0, h->stream));
     }
   }
-  h->gemm_stages = saved_stages;
   return 0;
 }
 
 int back_substitute(b200rbf_ctx* h, const double* A, int ld, int N, double* y, double* x, int* info_dev) {
-  static bool attr = false;
+  static DeviceOnce attr;
   const size_t smem = (size_t)kBsBlock * (kBsBlock + 1) * sizeof(double);
-  if (!attr) {
+  if (attr.pending(h->device)) {
     B2_CUDA(cudaFuncSetAttribute(diag_upper_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
+    attr.done(h->device);
   }
   const int nblk = (N + kBsBlock - 1) / kBsBlock;
   for (int b = nblk - 1; b >= 0; --b) {

@@ -236,10 +236,10 @@ template <int DPAD, int KERN, bool EXACT, bool WITH_PHI>
 int launch_score_inst(b200rbf_ctx* h, const ScoreArgs& a) {
   auto kern = score_kernel<DPAD, KERN, EXACT, WITH_PHI>;
   constexpr size_t smem = score_smem_bytes<DPAD>();
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.pending(h->device)) {
     B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_set.done(h->device);
   }
   if (a.occ_out != nullptr) {  // query only: resident CTAs per SM of this instantiation
     B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(a.occ_out, kern, kScoreThreads, smem));

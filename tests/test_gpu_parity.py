@@ -560,3 +560,22 @@ def test_predict_deriv_many_queries_uses_the_tile_kernel(pb, orc, kernel, tail, 
     assert relmax(small, ref) < TOL and relmax(big[:300], ref) < TOL
     ref_tail = o.predict_deriv(q[-50:])
     assert relmax(big[-50:], ref_tail) < TOL
+
+
+@pytest.mark.parametrize("d", [150, 170, 190])
+def test_fit_with_large_tail_dimension(pb, orc, d):
+    """the Cholesky fit's t x t helper kernels keep a (t rounded to 16)^2 matrix in shared memory, which
+    exceeds the 227 KB opt-in limit for d >= 160; those dimensions must take the pivoted LU instead of failing."""
+    rng = np.random.default_rng(d)
+    n = 2 * (d + 1) + 60
+    lb, ub = np.zeros(d), np.ones(d)
+    X = rng.random((n, d))
+    fX = np.sin(X.sum(1) / 7)[:, None]
+    s = make_gpu(pb, d, lb, ub, "cubic", "linear")
+    s.add_points(X, fX)
+    o = orc.OracleRBF(d, lb, ub, "cubic", "linear")
+    o.add_points(X, fX)
+    q = rng.random((64, d))
+    assert relmax(s.predict(q), o.predict(q)) < TOL
+    assert s.handle.last_fit_method == ("cholesky" if d < 160 else "lu")
+    assert relmax(s.predict_deriv(q[:4]), o.predict_deriv(q[:4])) < TOL

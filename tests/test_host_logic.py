@@ -171,6 +171,21 @@ def test_install_rebinds_reference_names():
         assert ss.candidate_srbf is cnd.candidate_srbf and cd.weighted_distance_merit is cnd.weighted_distance_merit
         assert so.nd_sorting is cnd.nd_sorting  # SOP's host bottleneck, numpy version with identical output
         assert len(done) >= 10
+        # after install() the reference's other surrogates still work -- a non-GPU surrogate is handed to
+        # the reference function that install() replaced (here: the stock CPU RBFInterpolant through candidate_dycors)
+        from pySOT.surrogate import RBFInterpolant
+
+        prob = Problem(np.zeros(3), np.ones(3))
+        rng = np.random.default_rng(0)
+        X, fX = rng.random((12, 3)), rng.random((12, 1))
+        cpu = RBFInterpolant(dim=3, lb=prob.lb, ub=prob.ub)
+        cpu.add_points(X, fX)
+        np.random.seed(5)
+        want = orig(num_pts=2, opt_prob=prob, surrogate=cpu, X=X, fX=fX, weights=[0.3, 0.8], prob_perturb=0.5, num_cand=50)
+        np.random.seed(5)
+        got = ds.candidate_dycors(num_pts=2, opt_prob=prob, surrogate=cpu, X=X, fX=fX, weights=[0.3, 0.8],
+                                  prob_perturb=0.5, num_cand=50)
+        assert np.array_equal(want, got)
     finally:
         cnd.uninstall()
     assert ds.candidate_dycors is orig

@@ -87,13 +87,12 @@ def replay(fname, backend, max_calls=None, timer=None):
         if "deriv" in g:  # config #5 add-on: value and gradient at every proposed point
             sl = slice(pt_off[i], pt_off[i + 1])
             gd, gp = s.predict_deriv(ref), s.predict(ref)
-            for key in ("deriv", "deriv_full"):
-                err[key] = max(err.get(key, 0.0), float(np.max(np.abs(gd - g[key][sl]))))
-            for key in ("pred", "pred_full"):
-                err[key] = max(err.get(key, 0.0), float(np.max(np.abs(gp - g[key][sl]))))
+            for key, got in (("deriv", gd), ("deriv_full", gd), ("pred", gp), ("pred_full", gp)):
+                if not np.isnan(g[key][sl]).any():  # the fresh-fit columns are recorded for a subset of the calls
+                    err[key] = max(err.get(key, 0.0), float(np.max(np.abs(got - g[key][sl]))))
     if err:  # max |delta| / max |reference| over the whole trace (the north-star parity metric)
         n_used = pt_off[ncalls]
-        sd, sp = float(np.max(np.abs(g["deriv_full"][:n_used]))), float(np.max(np.abs(g["pred_full"][:n_used])))
+        sd, sp = float(np.nanmax(np.abs(g["deriv_full"][:n_used]))), float(np.nanmax(np.abs(g["pred_full"][:n_used])))
         err = {"pred_vs_incremental": err["pred"] / sp, "deriv_vs_incremental": err["deriv"] / sd,
                "pred_vs_fresh_fit": err["pred_full"] / sp, "deriv_vs_fresh_fit": err["deriv_full"] / sd}
     return ncalls, mismatches, ties, err

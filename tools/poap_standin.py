@@ -12,11 +12,16 @@ in `docs/poap.rst:34-101` and visible at their call sites (`surrogate_strategy.p
   SimAsyncController            deterministic emulation of ThreadController with W workers: proposals are
                                 accepted while a worker is free, otherwise the OLDEST running evaluation
                                 completes (so up to W-1 points are pending when a proposal is generated)
+  ThreadController              real threads: workers evaluate concurrently and report through a message queue that
+  BasicWorkerThread             only the controller thread drains, so strategy / surrogate code runs on ONE thread
+                                while objectives run on the others (docs/poap.rst:54-63, tests/test_strategies.py:60-82)
 
 Install with `install()` BEFORE importing pySOT so that `from poap.strategy import BaseStrategy, Proposal`
 resolves here.
 """
+import queue
 import sys
+import threading
 import types
 
 
@@ -183,6 +188,107 @@ class SimAsyncController(Controller):
             p.accept()
             r.running()
             self.running.append(r)
+
+
+class ThreadController(Controller):
+    """Threaded controller (docs/poap.rst:54-63).  Idle workers wait in ``self.workers``; anything that touches a record or
+    the strategy is posted as a closure to ``self.messages`` and executed by ``run()`` on the caller's thread.
+
+    Loop: drain the queued messages, ask the strategy for a proposal;  no proposal -> block for one message;
+    ``terminate`` -> accept and stop;  ``eval`` with an idle worker -> new record, accept, hand the record to the worker;
+    anything else -> reject and block for one message (so a strategy that always proposes does not spin)."""
+
+    def __init__(self):
+        super().__init__()
+        self.workers = queue.Queue()
+        self.messages = queue.Queue()
+        self._threads = []
+
+    def add_worker(self, worker):
+        self.workers.put(worker)
+
+    def launch_worker(self, worker, daemon=True):
+        worker.daemon = daemon
+        self._threads.append(worker)
+        self.add_worker(worker)
+        worker.start()
+
+    def add_message(self, message=None):
+        self.messages.put(message)
+
+    def can_work(self):
+        return not self.workers.empty()
+
+    def _run_message(self):
+        message = self.messages.get()  # blocks
+        if message is not None:
+            message()
+
+    def _run_queued_messages(self):
+        while True:
+            try:
+                message = self.messages.get_nowait()
+            except queue.Empty:
+                return
+            if message is not None:
+                message()
+
+    def run(self):
+        try:
+            while True:
+                self._run_queued_messages()
+                p = self.strategy.propose_action()
+                if p is None:
+                    self._run_message()
+                elif p.action == "terminate":
+                    p.accept()
+                    return self._terminate()
+                elif p.action == "eval" and self.can_work():
+                    worker = self.workers.get_nowait()
+                    r = self.new_feval(p.args)
+                    r.worker = worker
+                    p.record = r
+                    p.accept()
+                    worker.eval(r)
+                else:
+                    p.reject()
+                    self._run_message()
+        finally:
+            for w in self._threads:
+                w.terminate()
+
+
+class BasicWorkerThread(threading.Thread):
+    """Worker that calls a Python objective on its own thread (tests/test_strategies.py:62-64).  Record updates are
+    never made here: they are posted to the controller as messages.  An objective that raises kills the record."""
+
+    def __init__(self, controller, objective):
+        super().__init__()
+        self.controller, self.objective = controller, objective
+        self.requests = queue.Queue()
+
+    def eval(self, record):
+        self.requests.put(("eval", record))
+
+    def kill(self, record):  # a Python call cannot be interrupted; POAP's basic worker ignores kill requests too
+        pass
+
+    def terminate(self):
+        self.requests.put(("terminate", None))
+
+    def run(self):
+        while True:
+            what, record = self.requests.get()
+            if what == "terminate":
+                return
+            self.controller.add_message(record.running)
+            try:
+                value = self.objective(*record.params)
+            except Exception:
+                self.controller.add_message(record.kill)
+            else:
+                self.controller.add_message(lambda r=record, v=value: r.complete(v))
+            self.controller.add_worker(self)  # idle again, after its result was posted
 
 
 def install():
