@@ -37,7 +37,8 @@ enum {
   B200RBF_ECUDA = -2,     /* CUDA runtime failure */
   B200RBF_ESTATE = -3,    /* call order: no model loaded / nothing scored */
   B200RBF_ESINGULAR = -4, /* exactly singular pivot in the saddle-point LU */
-  B200RBF_ENOMEM = -5
+  B200RBF_ENOMEM = -5,
+  B200RBF_EREFIT = -6     /* b200rbf_extend only: nothing extendable resident / budget used up / pivot failed: call b200rbf_fit */
 };
 
 /* options for b200rbf_set_option */
@@ -62,7 +63,10 @@ enum {
   B200RBF_OPT_MMA_DIST = 6,
   /* solver of b200rbf_fit: 0 (default) auto = null-space Cholesky for cubic / TPS + linear tail with n >= 128, pivoted
    *    LU otherwise and whenever the Cholesky reports a non-positive pivot; 1 = always LU; 2 = Cholesky or error       */
-  B200RBF_OPT_FIT_METHOD = 7
+  B200RBF_OPT_FIT_METHOD = 7,
+  /* 1 (default): a Cholesky fit of n <= 8192 points pre-allocates room for 2 n (at least 1024) so that b200rbf_extend
+   *    can append points in place; 0: never keep an extendable factorisation                                      */
+  B200RBF_OPT_INCREMENTAL = 8
 };
 
 const char* b200rbf_last_error(void);
@@ -89,6 +93,18 @@ int b200rbf_set_option(b200rbf_handle h, int option, long long value);
  * fit_seconds (optional): device time of assembly + factorisation + solves (CUDA events). */
 int b200rbf_fit(b200rbf_handle h, const double* Xu, const double* rhs, int n, int d, int kernel, int tail,
                 double eta, double* c_out, double* fit_seconds);
+
+/* RBFInterpolant._fit, incremental branch (rbf.py:132-161): the resident model was fitted (b200rbf_fit, Cholesky solver)
+ * or extended for the first n_old rows of Xu, and rows n_old .. n are new points.  The reference extends its LU factors by
+ * the new rows / columns and a Cholesky factorisation of their Schur complement, O(k n^2); here the null-space Cholesky
+ * factor grows by one row per point (fit_extend.cu), pre-allocated -- no O(n^2) regrowth -- and resident on the device.
+ * Xu: ALL n points (only the new rows are read); rhs: all n transformed values; rhs_changed != 0: the values of old
+ * points differ from the previous call (e.g. median capping moved), so the right-hand side is re-projected.
+ * Returns B200RBF_EREFIT -- and leaves the decision to the caller, exactly like the fallback at rbf.py:149-153 -- when
+ * there is no extendable factorisation, the point count exceeds the pre-allocated capacity or 4 x the base size (the
+ * null-space basis is re-orthogonalised by a full fit then), or a new pivot is not positive.  last_fit_method = 3. */
+int b200rbf_extend(b200rbf_handle h, const double* Xu, const double* rhs, int n, int rhs_changed, double* c_out,
+                   double* fit_seconds);
 
 /* Make centers + coefficients resident without fitting (replica GPUs of the sharded scoring path, or a
  * model restored from a pickle).  c: n + ntail, tail first. */
@@ -159,7 +175,7 @@ long long b200rbf_launch_count(b200rbf_handle h);
 /* Device time (ms, CUDA events on the handle's stream) of the fused score kernel(s) of the last b200rbf_score;
  * with host candidates it spans the chunk pipeline including the waits on the H2D copies. */
 double b200rbf_last_score_ms(b200rbf_handle h);
-/* Solver the last b200rbf_fit used: 1 = pivoted LU, 2 = null-space Cholesky. */
+/* Solver the last b200rbf_fit / b200rbf_extend used: 1 = pivoted LU, 2 = null-space Cholesky, 3 = row-append extension. */
 int b200rbf_last_fit_method(b200rbf_handle h);
 
 /* ---- test hooks: exercise the factorisation pieces in isolation (tests/ only, not the drop-in surface) ----

@@ -13,7 +13,8 @@ LIB_PATH = os.path.join(_HERE, "libb200rbf.so")
 KERNEL_CUBIC, KERNEL_TPS, KERNEL_LINEAR = 0, 1, 2
 TAIL_LINEAR, TAIL_CONSTANT = 0, 1
 OPT_EXACT_DIST, OPT_CHUNK_ROWS, OPT_LU_PANEL, OPT_LU_LOOKAHEAD, OPT_GEMM_STAGES, OPT_MMA_DIST, OPT_FIT_METHOD = 1, 2, 3, 4, 5, 6, 7
-E_INVAL, E_CUDA, E_STATE, E_SINGULAR, E_NOMEM = -1, -2, -3, -4, -5
+OPT_INCREMENTAL = 8
+E_INVAL, E_CUDA, E_STATE, E_SINGULAR, E_NOMEM, E_REFIT = -1, -2, -3, -4, -5, -6
 
 _dp = C.POINTER(C.c_double)
 _vp = C.c_void_p
@@ -27,6 +28,7 @@ PROTOTYPES = {
     "b200rbf_set_stream": (C.c_int, [_vp, _vp, C.c_int]),
     "b200rbf_set_option": (C.c_int, [_vp, C.c_int, C.c_longlong]),
     "b200rbf_fit": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _vp, _dp]),
+    "b200rbf_extend": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _dp]),
     "b200rbf_load": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int]),
     "b200rbf_predict": (C.c_int, [_vp, _vp, C.c_longlong, _vp, _vp, _vp]),
     "b200rbf_predict_deriv": (C.c_int, [_vp, _vp, C.c_longlong, _vp, _vp, _vp]),
@@ -140,7 +142,7 @@ class Handle:
 
     @property
     def last_fit_method(self):
-        return {1: "lu", 2: "cholesky"}.get(int(load().b200rbf_last_fit_method(self._h)), "none")
+        return {1: "lu", 2: "cholesky", 3: "extension"}.get(int(load().b200rbf_last_fit_method(self._h)), "none")
 
     # ---- model
     def fit(self, Xu, rhs, kernel, tail, eta):
@@ -150,6 +152,20 @@ class Handle:
         c = np.empty(n + nt)
         secs = C.c_double(0.0)
         check(load().b200rbf_fit(self._h, ptr(Xu), ptr(rhs), n, d, kernel, tail, float(eta), ptr(c), C.byref(secs)))
+        return c, secs.value
+
+    def extend(self, Xu, rhs, tail, rhs_changed=False):
+        """Append the rows of Xu beyond the resident point count (rbf.py:132-161).  Returns (c, seconds), or None when the
+        library asks for a full refit (nothing extendable resident, budget used up, pivot failed)."""
+        Xu, rhs = f64(Xu), f64(rhs).ravel()
+        n, d = Xu.shape
+        nt = d + 1 if tail == TAIL_LINEAR else 1
+        c = np.empty(n + nt)
+        secs = C.c_double(0.0)
+        code = load().b200rbf_extend(self._h, ptr(Xu), ptr(rhs), n, 1 if rhs_changed else 0, ptr(c), C.byref(secs))
+        if code == E_REFIT:
+            return None
+        check(code)
         return c, secs.value
 
     def load_model(self, Xu, c, kernel, tail):

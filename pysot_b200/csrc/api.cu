@@ -15,9 +15,12 @@ void set_error(const char* fmt, ...) {
 
 int deriv_scratch_doubles(const b200rbf_ctx* h, long long m, size_t* out);
 int chol_fit_weights(b200rbf_ctx* h, const double* Xu_dev, const double* f_dev, int n, int d, int kernel, double eta,
-                     CholWork* wk, int* info_dev);
+                     CholWork* wk, int* info_dev, int cap_rows);
 int chol_fit_tail(b200rbf_ctx* h, const CholWork& w, const double* f_dev, const double* g_dev, double eta,
-                  double* c_full_dev);
+                  double* c_full_dev, int n_base, int n_all);
+int chol_extend_weights(b200rbf_ctx* h, const double* f_dev, int n, bool rhs_changed, int* info_dev);
+int ext_refresh_rhs(b200rbf_ctx* h, const double* f_dev);
+int trsv_sync_error(b200rbf_ctx* h, unsigned* err_host);
 int run_generate(b200rbf_ctx* h, int kind, long long m, int d, const double* xbest, const double* lb, const double* ub,
                  const double* sigma, double prob_perturb, const int* subset, int nsub, const unsigned char* int_mask,
                  unsigned long long seed, double* cand_dev);
@@ -440,6 +443,7 @@ int b200rbf_destroy(b200rbf_handle h) {
   S.stats.release(); S.winner.release(); S.results.release(); S.dist.release(); S.box.release();
   FitState& F = h->fit;
   F.A.release(); F.piv.release(); F.rhs.release(); F.work.release(); F.flags.release(); F.chol.release();
+  F.sync.release(); F.ext.Xu.release();
   h->tmp_in.release(); h->tmp_out.release(); h->tmp_box.release(); h->gen_buf.release(); h->gen_pin.release();
   h->tps_table.release();
   h->stage[0].release(); h->stage[1].release(); h->pin_small.release();
@@ -477,6 +481,10 @@ int b200rbf_set_option(b200rbf_handle h, int option, long long value) {
       h->chunk_rows = value;
       return 0;
     case B200RBF_OPT_LU_LOOKAHEAD: h->lu_lookahead = value != 0; return 0;
+    case B200RBF_OPT_INCREMENTAL:
+      h->incremental = value != 0;
+      if (!h->incremental) h->fit.ext.valid = false;
+      return 0;
     case B200RBF_OPT_GEMM_STAGES:
       B2_CHECK(value == 0 || (value >= 2 && value <= 4), B200RBF_EINVAL, "GEMM variant must be 0 (auto), 2, 3 or 4");
       h->gemm_stages_auto = value == 0;
@@ -505,6 +513,7 @@ int b200rbf_load(b200rbf_handle h, const double* Xu, const double* c, int n, int
   double* cd = Xd + (size_t)n * d;
   B2_TRY(copy_in(h, Xd, Xu, (size_t)n * d * sizeof(double)));
   B2_TRY(copy_in(h, cd, c, (size_t)(n + t) * sizeof(double)));
+  h->fit.ext.valid = false;  // the resident factorisation (if any) no longer belongs to the resident model
   B2_TRY(install_model(h, Xd, cd, n, d, kernel, tail));
   B2_CUDA(cudaStreamSynchronize(h->stream));
   return 0;
@@ -538,12 +547,18 @@ int b200rbf_fit(b200rbf_handle h, const double* Xu, const double* rhs, int n, in
   B2_CHECK(h->fit_method != 2 || chol_ok, B200RBF_EINVAL,
            "the Cholesky fit needs a cubic / TPS kernel with the linear tail, n >= 2 ntail + 32 and dim <= 159");
   bool done = false;
+  ExtState& E = h->fit.ext;
+  E.valid = false;
   if (chol_ok && (h->fit_method == 2 || (h->fit_method == 0 && n >= 128))) {
     B2_TRY(h->fit.piv.reserve(256));
     int* info_dev = h->fit.piv.as<int>();
     B2_CUDA(cudaMemsetAsync(info_dev, 0, sizeof(int), h->stream));
     CholWork wk;
-    B2_TRY(chol_fit_weights(h, Xd, rd, n, d, kernel, eta, &wk, info_dev));
+    // room for b200rbf_extend to append points in place: twice the rows (at least 1024), for the sizes where a refit
+    // per added point is what a strategy would otherwise pay (rbf.py:132-161)
+    int cap = 0;
+    if (h->incremental && n <= kExtMaxBase) cap = 2 * n < 1024 ? 1024 : ((2 * n + 127) / 128) * 128;
+    B2_TRY(chol_fit_weights(h, Xd, rd, n, d, kernel, eta, &wk, info_dev, cap));
     // (Phi + eta I) c for the tail: evaluate the weights-only model at its own centers with the fused score kernel
     B2_CUDA(cudaMemsetAsync(cd, 0, (size_t)t * sizeof(double), h->stream));
     B2_CUDA(cudaMemcpyAsync(cd + t, wk.v2, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
@@ -555,12 +570,28 @@ int b200rbf_fit(b200rbf_handle h, const double* Xu, const double* rhs, int n, in
     double* g = parts + (size_t)4 * np;
     ScorePlan plan;
     B2_TRY(score_rows(h, plan, Xd, 0, n, nullptr, g, nullptr, parts, np, 0, 0));
-    B2_TRY(chol_fit_tail(h, wk, rd, g, eta, cd));
+    B2_TRY(chol_fit_tail(h, wk, rd, g, eta, cd, n, n));
+    if (cap > 0) {
+      B2_TRY(E.Xu.reserve((size_t)cap * d * sizeof(double)));
+      B2_CUDA(cudaMemcpyAsync(E.Xu.p, Xd, (size_t)n * d * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    unsigned* sync_err = reinterpret_cast<unsigned*>(info_host + 1);
+    B2_TRY(trsv_sync_error(h, sync_err));
     B2_CUDA(cudaMemcpyAsync(info_host, info_dev, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     B2_CUDA(cudaStreamSynchronize(h->stream));
+    B2_CHECK(*sync_err == 0, B200RBF_ECUDA, "triangular solve: a block waited too long for its predecessor");
     if (*info_host == 0) {
       done = true;
       h->last_fit_method = 2;
+      if (cap > 0) {
+        E.valid = true;
+        E.n0 = E.N = n;
+        E.cap = cap;
+        E.d = d;
+        E.kernel = kernel;
+        E.eta = eta;
+        E.w = wk;
+      }
     } else {
       B2_CHECK(h->fit_method != 2, B200RBF_ESINGULAR,
                "Cholesky fit failed (%s step, index %d): projected matrix not numerically positive definite",
@@ -586,6 +617,68 @@ int b200rbf_fit(b200rbf_handle h, const double* Xu, const double* rhs, int n, in
     set_error("singular matrix: exactly zero pivot at diagonal %d of the saddle-point system", *info_host);
     return B200RBF_ESINGULAR;
   }
+  return 0;
+}
+
+int b200rbf_extend(b200rbf_handle h, const double* Xu, const double* rhs, int n, int rhs_changed, double* c_out,
+                   double* fit_seconds) {
+  B2_CHECK(h && Xu && rhs, B200RBF_EINVAL, "NULL argument");
+  ExtState& E = h->fit.ext;
+  Model& M = h->model;
+  // not extendable -> the caller does a full b200rbf_fit (which also re-orthogonalises the null-space basis)
+  B2_CHECK(E.valid && M.loaded && M.n == E.N && M.d == E.d, B200RBF_EREFIT, "no extendable factorisation resident");
+  B2_CHECK(n > E.N, B200RBF_EREFIT, "no new points (resident %d, given %d)", E.N, n);
+  B2_CHECK(n <= E.cap && n <= kExtGrowth * E.n0, B200RBF_EREFIT,
+           "%d points exceed the extension budget (capacity %d, %d x base %d)", n, E.cap, kExtGrowth, E.n0);
+  B2_CUDA(cudaSetDevice(h->device));
+  const int d = E.d, t = d + 1, N = n + t, n_old = E.N;
+  B2_TRY(h->tmp_in.reserve(((size_t)n + N) * sizeof(double)));
+  double* rd = h->tmp_in.as<double>();
+  double* cd = rd + n;
+  B2_TRY(h->pin_small.reserve(4096 * sizeof(double)));
+  B2_CUDA(cudaStreamSynchronize(h->stream));
+  int* info_host = reinterpret_cast<int*>(h->pin_small.p);
+  unsigned* sync_err = reinterpret_cast<unsigned*>(info_host + 1);
+  *info_host = 0;
+  double* Xall = E.Xu.as<double>();
+  B2_TRY(copy_in(h, Xall + (size_t)n_old * d, Xu + (size_t)n_old * d, (size_t)(n - n_old) * d * sizeof(double)));
+  B2_TRY(copy_in(h, rd, rhs, (size_t)n * sizeof(double)));
+  B2_CUDA(cudaEventRecord(h->ev_t0, h->stream));
+  int* info_dev = h->fit.piv.as<int>();
+  B2_CUDA(cudaMemsetAsync(info_dev, 0, sizeof(int), h->stream));
+  E.valid = false;  // until this extension has been checked
+  B2_TRY(chol_extend_weights(h, rd, n, rhs_changed != 0, info_dev));
+  // tail exactly as in the full fit, over the base points: lambda = R0^-1 Q0^T (f_0 - ((Phi + eta I) c)_0)
+  B2_CUDA(cudaMemsetAsync(cd, 0, (size_t)t * sizeof(double), h->stream));
+  B2_CUDA(cudaMemcpyAsync(cd + t, E.w.v2, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  B2_TRY(install_model(h, Xall, cd, n, d, E.kernel, B200RBF_TAIL_LINEAR));
+  const int br = block_rows(h->model.dpad);
+  const int np = (E.n0 + br - 1) / br + 8;
+  B2_TRY(h->tmp_out.reserve(((size_t)4 * np + E.n0 + 16) * sizeof(double)));
+  double* parts = h->tmp_out.as<double>();
+  double* g = parts + (size_t)4 * np;
+  ScorePlan plan;
+  B2_TRY(score_rows(h, plan, Xall, 0, E.n0, nullptr, g, nullptr, parts, np, 0, 0));
+  B2_TRY(chol_fit_tail(h, E.w, rd, g, E.eta, cd, E.n0, n));
+  B2_TRY(install_model(h, Xall, cd, n, d, E.kernel, B200RBF_TAIL_LINEAR));
+  B2_CUDA(cudaEventRecord(h->ev_t1, h->stream));
+  if (c_out) B2_TRY(copy_out(h, c_out, cd, (size_t)N * sizeof(double)));
+  B2_TRY(trsv_sync_error(h, sync_err));
+  B2_CUDA(cudaMemcpyAsync(info_host, info_dev, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  B2_CUDA(cudaStreamSynchronize(h->stream));
+  if (fit_seconds) {
+    float ms = 0.f;
+    B2_CUDA(cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1));
+    *fit_seconds = ms * 1e-3;
+  }
+  B2_CHECK(*sync_err == 0, B200RBF_ECUDA, "triangular solve: a block waited too long for its predecessor");
+  if (*info_host != 0) {  // rbf.py:149-153: the Cholesky of the new points' Schur complement failed -> full refit
+    h->model.loaded = false;
+    set_error("extension failed at point %d: not numerically positive definite", *info_host - 1);
+    return B200RBF_EREFIT;
+  }
+  E.valid = true;
+  h->last_fit_method = 3;
   return 0;
 }
 

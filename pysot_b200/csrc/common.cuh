@@ -170,6 +170,33 @@ struct ScoreState {
   DevBuf box;               // 2 x dpad : lb, (ub - lb)
 };
 
+
+// views into FitState::chol for one null-space Cholesky fit (P, W, Linv and the vectors are sized for `rows_cap` rows
+// when the factorisation may be extended by fit_extend.cu)
+struct CholWork {
+  double *P, *Qneg, *W, *Acat, *Bcat, *T21, *Linv, *LinvT, *Tn, *G, *R1, *R2, *R, *S, *gpart, *v0, *v1, *v2, *q;
+  double *Rinv, *fq, *bvec, *u, *mrow, *gbuf;  // extension state: R^-1, Q0^T f_0, T^T f, L^-1 T^T f, scratch rows
+  int n, n16, t, tp, ld;
+};
+
+// flags of the single-launch pipelined triangular solves (fit_extend.cu)
+constexpr int kExtMaxBase = 8192;    // largest point count whose factorisation is kept extendable (capacity 2x)
+constexpr int kExtGrowth = 4;        // refit from scratch once the point count exceeds this multiple of the base
+constexpr int kTrsvMaxBlocks = 160;  // x 128 rows = 20 480
+struct TrsvSync {
+  unsigned ticket, done, err, pad;
+  unsigned flag[kTrsvMaxBlocks];
+};
+
+// what b200rbf_extend needs from the last null-space Cholesky fit (base points 0 .. n0) and the points appended since
+struct ExtState {
+  bool valid = false;
+  int n0 = 0, N = 0, cap = 0, d = 0, kernel = 0;
+  double eta = 0.0;
+  CholWork w;
+  DevBuf Xu;  // cap x d unit-box coordinates of all resident points
+};
+
 struct FitState {
   DevBuf A;      // N x ld saddle-point matrix, row-major, overwritten by L\U
   DevBuf piv;    // N int pivot rows
@@ -177,12 +204,9 @@ struct FitState {
   DevBuf work;   // cooperative panel scratch
   DevBuf flags;
   DevBuf chol;   // workspace of the null-space Cholesky fit (fit_chol.cu)
-};
-
-// views into FitState::chol for one null-space Cholesky fit
-struct CholWork {
-  double *P, *Qneg, *W, *Acat, *Bcat, *T21, *Linv, *LinvT, *Tn, *G, *R1, *R2, *R, *S, *gpart, *v0, *v1, *v2, *q;
-  int n, n16, t, tp, ld;
+  DevBuf sync;   // TrsvSync
+  unsigned trsv_epoch = 0;
+  ExtState ext;
 };
 
 }  // namespace b200rbf
@@ -211,6 +235,7 @@ struct b200rbf_ctx {
   bool mma_dist = true;  // norm-expansion distances on the FP64 tensor path (score_mma.cuh) unless exact_dist
   long long chunk_rows = 131072;  // target rows per H2D chunk; rounded to whole waves of the score kernel
   int lu_panel = 128;
+  bool incremental = true;  // keep the Cholesky factorisation extendable by b200rbf_extend (pre-allocates 2x rows, n <= 8192)
   b200rbf::Model model;
   b200rbf::ScoreState score;
   b200rbf::FitState fit;

@@ -31,6 +31,9 @@ int gemm_sub_ex(b200rbf_ctx* h, double* C, int ldc, const double* A, int lda, co
 int assemble_plain(b200rbf_ctx* h, const double* Xu_dev, int n, int d, int kernel, double eta, double* A, int ld,
                    int ncols);
 int strip_gemv(b200rbf_ctx* h, const double* A, int ld, int r0, int rows, int c0, int c1, const double* x, double* y);
+int trsv_pipelined(b200rbf_ctx* h, const double* L, int ld, const double* Linv, int N, const double* b, double* x,
+                   bool transpose);
+int ext_make_rinv(b200rbf_ctx* h, const CholWork& w);
 
 namespace {
 
@@ -611,27 +614,32 @@ int gram(b200rbf_ctx* h, const double* X, const double* Y, int n, int tp, double
 }  // namespace
 
 // c_rbf (n) <- RBF weights; keeps Q, R in the workspace for the tail step.  info_dev: 0 ok, != 0 -> fall back to LU.
+// cap_rows > n: the factor, Q / W, the diagonal-block inverses and the vectors are laid out for cap_rows rows so that
+// fit_extend.cu can append points to this factorisation in place (no regrowth, no copies).
 int chol_fit_weights(b200rbf_ctx* h, const double* Xu_dev, const double* f_dev, int n, int d, int kernel, double eta,
-                     CholWork* wk, int* info_dev) {
+                     CholWork* wk, int* info_dev, int cap_rows) {
   FitState& F = h->fit;
-  const int t = d + 1, tp = (t + 15) & ~15, n16 = (n + 31) & ~31, ld = n16;  // n16: padded to the 32-column sub-blocks
+  const int t = d + 1, tp = (t + 15) & ~15, n16 = (n + 31) & ~31;  // n16: padded to the 32-column sub-blocks
+  const int rcap = cap_rows > n16 ? ((cap_rows + kNB - 1) / kNB) * kNB : n16, ld = rcap;
   const int nparts = (n + 63) / 64;
   size_t need = 0;
   auto take = [&](size_t cnt) { size_t off = need; need += (cnt + 15) & ~(size_t)15; return off; };
-  const size_t oP = take((size_t)n16 * tp), oQn = take((size_t)n16 * tp), oW = take((size_t)n16 * tp);
+  const size_t oP = take((size_t)rcap * tp), oQn = take((size_t)n16 * tp), oW = take((size_t)rcap * tp);
   const size_t oAc = take((size_t)n16 * 3 * tp), oBc = take((size_t)3 * tp * ld), oT21 = take((size_t)kOuter * ld);
   const size_t oG = take((size_t)tp * tp), oR1 = take((size_t)tp * tp);
   const size_t oR2 = take((size_t)tp * tp), oR = take((size_t)tp * tp), oS = take((size_t)tp * tp);
-  const size_t oGp = take((size_t)nparts * tp * tp), oV0 = take(n16), oV1 = take(n16), oV2 = take(n16), oq = take(tp);
-  const size_t oLi = take((size_t)((n16 + kNB - 1) / kNB) * kNB * kNB), oLiT = take((size_t)kNB * kNB);
+  const size_t oGp = take((size_t)nparts * tp * tp), oV0 = take(rcap), oV1 = take(rcap), oV2 = take(rcap), oq = take(tp);
+  const size_t oLi = take((size_t)((rcap + kNB - 1) / kNB) * kNB * kNB), oLiT = take((size_t)kNB * kNB);
   const size_t oTn = take((size_t)n16 * kNB);
+  const size_t oRi = take((size_t)tp * tp), oFq = take(tp), oBv = take(rcap), oU = take(rcap), oMr = take(rcap), oGb = take(rcap);
   B2_TRY(F.chol.reserve(need * sizeof(double)));
-  B2_TRY(F.A.reserve(((size_t)n16 * ld + 1024) * sizeof(double)));
+  B2_TRY(F.A.reserve(((size_t)rcap * ld + 1024) * sizeof(double)));
   double* base = F.chol.as<double>();
   CholWork& w = *wk;
   w.P = base + oP; w.Qneg = base + oQn; w.W = base + oW; w.Acat = base + oAc; w.Bcat = base + oBc; w.T21 = base + oT21;
   w.G = base + oG; w.R1 = base + oR1; w.R2 = base + oR2; w.R = base + oR; w.S = base + oS;
   w.Linv = base + oLi; w.LinvT = base + oLiT; w.Tn = base + oTn; w.gpart = base + oGp; w.v0 = base + oV0; w.v1 = base + oV1; w.v2 = base + oV2; w.q = base + oq;
+  w.Rinv = base + oRi; w.fq = base + oFq; w.bvec = base + oBv; w.u = base + oU; w.mrow = base + oMr; w.gbuf = base + oGb;
   w.n = n; w.n16 = n16; w.t = t; w.tp = tp; w.ld = ld;
   double* A = F.A.as<double>();
   double* Q = w.P;  // P is orthonormalised in place
@@ -719,46 +727,33 @@ int chol_fit_weights(b200rbf_ctx* h, const double* Xu_dev, const double* f_dev, 
       B2_TRY(gemm_sub_ex(h, A + (size_t)R0 * ld + R0, ld, A + (size_t)R0 * ld + J0, ld, w.T21 + R0, ld, n16 - R0, n16 - R0,
                          R0 - J0, 1));
   }
-  // 6. c = Pi L^-T L^-1 Pi f
-  copy_pad_kernel<<<(n16 + 255) / 256, 256, 0, h->stream>>>(f_dev, n, w.v0, n16);
+  // 6. c = Pi L^-T L^-1 Pi f : two single-launch pipelined triangular solves (fit_extend.cu) with the stored inverses
+  // of the diagonal blocks.  bvec = Pi f and u = L^-1 Pi f are kept: an extension appends to them.
+  copy_pad_kernel<<<(n16 + 255) / 256, 256, 0, h->stream>>>(f_dev, n, w.bvec, n16);
   LAUNCHED(h);
-  qt_vec_kernel<<<1, 1024, 0, h->stream>>>(Q, n, tp, w.v0, w.q);
+  qt_vec_kernel<<<1, 1024, 0, h->stream>>>(Q, n, tp, w.bvec, w.fq);
   LAUNCHED(h);
-  sub_q_kernel<<<(n16 + 255) / 256, 256, 0, h->stream>>>(Q, n, tp, w.q, w.v0, n16);
+  sub_q_kernel<<<(n16 + 255) / 256, 256, 0, h->stream>>>(Q, n, tp, w.fq, w.bvec, n16);
   LAUNCHED(h);
-  const size_t sm_blk = (size_t)kNB * (kNB + 1) * sizeof(double);
-  B2_CUDA(cudaFuncSetAttribute(block_matvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_blk));
-  const int nblk = (n16 + kNB - 1) / kNB;
-  for (int b = 0; b < nblk; ++b) {  // forward: L y = b   (y in v1), right-looking: every row below updates in parallel
-    const int r0 = b * kNB, rows = (n16 - r0 < kNB) ? (n16 - r0) : kNB;
-    block_matvec_kernel<<<1, kMvThreads, sm_blk, h->stream>>>(w.Linv + (size_t)b * kNB * kNB, rows, w.v0 + r0, w.v1 + r0, 0);
-    LAUNCHED(h);
-    B2_TRY(strip_gemv(h, A, ld, r0 + rows, n16 - r0 - rows, r0, r0 + rows, w.v1, w.v0));
-  }
-  for (int b = nblk - 1; b >= 0; --b) {  // backward: L^T x = y   (x in v2, y consumed in v1)
-    const int r0 = b * kNB, rows = (n16 - r0 < kNB) ? (n16 - r0) : kNB;
-    block_matvec_kernel<<<1, kMvThreads, sm_blk, h->stream>>>(w.Linv + (size_t)b * kNB * kNB, rows, w.v1 + r0, w.v2 + r0, 1);
-    LAUNCHED(h);
-    if (r0 > 0) {
-      col_update_kernel<<<(r0 + 31) / 32, dim3(32, 8), 0, h->stream>>>(A, ld, r0, rows, r0, w.v2, w.v1);
-      LAUNCHED(h);
-    }
-  }
+  B2_TRY(trsv_pipelined(h, A, ld, w.Linv, n, w.bvec, w.u, false));
+  B2_TRY(trsv_pipelined(h, A, ld, w.Linv, n, w.u, w.v2, true));
   qt_vec_kernel<<<1, 1024, 0, h->stream>>>(Q, n, tp, w.v2, w.q);
   LAUNCHED(h);
   sub_q_kernel<<<(n16 + 255) / 256, 256, 0, h->stream>>>(Q, n, tp, w.q, w.v2, n16);
   LAUNCHED(h);
+  if (cap_rows > 0) B2_TRY(ext_make_rinv(h, w));
   return 0;  // RBF weights in w.v2[0 .. n)
 }
 
 // lambda and the final coefficient vector: g = Phi c (without eta) evaluated by the caller
+// n_base: the points P = Q R was factored for (rows of Q); n_all >= n_base: all points carrying a weight in w.v2
 int chol_fit_tail(b200rbf_ctx* h, const CholWork& w, const double* f_dev, const double* g_dev, double eta,
-                  double* c_full_dev) {
-  residual_kernel<<<(w.n + 255) / 256, 256, 0, h->stream>>>(f_dev, g_dev, w.v2, eta, w.n, w.v0);
+                  double* c_full_dev, int n_base, int n_all) {
+  residual_kernel<<<(n_base + 255) / 256, 256, 0, h->stream>>>(f_dev, g_dev, w.v2, eta, n_base, w.v0);
   LAUNCHED(h);
-  qt_vec_kernel<<<1, 1024, 0, h->stream>>>(w.P, w.n, w.tp, w.v0, w.q);
+  qt_vec_kernel<<<1, 1024, 0, h->stream>>>(w.P, n_base, w.tp, w.v0, w.q);
   LAUNCHED(h);
-  tail_finish_kernel<<<1, 256, (size_t)w.tp * sizeof(double), h->stream>>>(w.R, w.tp, w.t, w.q, w.v2, w.n, c_full_dev);
+  tail_finish_kernel<<<1, 256, (size_t)w.tp * sizeof(double), h->stream>>>(w.R, w.tp, w.t, w.q, w.v2, n_all, c_full_dev);
   LAUNCHED(h);
   return 0;
 }

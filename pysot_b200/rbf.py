@@ -27,15 +27,18 @@ class GpuRBFInterpolant(_Base):
     :param dim, lb, ub, output_transformation, kernel, tail, eta: as in the reference (rbf.py:67)
     :param device: CUDA ordinal (default: LOCAL_RANK or 0)
     :param exact_dist: accumulate squared distances with separate multiply and add exactly like
-        scipy's cdist instead of fused multiply-add (bit-identical distances, ~1.4x slower inner loop)
+        scipy's cdist instead of fused multiply-add (bit-identical distances, ~2.5x slower scoring)
+    :param incremental: extend the resident factorisation when points are added (rbf.py:132-161) instead of
+        refitting from scratch; False = every ``_fit`` is a fresh fit
 
-    Differences a user can observe: ``A``, ``L``, ``U``, ``piv`` stay ``None`` (the factors live on the
-    device and every ``_fit`` is a fresh pivoted LU there instead of the incremental update of rbf.py:132-161),
-    and kernels / tails other than the reference's five classes raise ``NotImplementedError``.
+    Differences a user can observe: ``A``, ``L``, ``U``, ``piv`` stay ``None`` (the factors live on the device:
+    a null-space Cholesky factorisation for cubic / TPS + linear tail, extended row by row as points arrive,
+    a pivoted LU otherwise), and kernels / tails other than the reference's five classes raise
+    ``NotImplementedError``.
     """
 
     def __init__(self, dim, lb, ub, output_transformation=None, kernel=None, tail=None, eta=1e-6, device=None,
-                 exact_dist=False):
+                 exact_dist=False, incremental=True):
         if HAVE_PYSOT:
             super().__init__(dim=dim, lb=lb, ub=ub, output_transformation=output_transformation, kernel=kernel,
                              tail=tail, eta=eta)
@@ -58,7 +61,10 @@ class GpuRBFInterpolant(_Base):
         self._device = default_device() if device is None else int(device)
         self._exact = bool(exact_dist)
         self._handle = None
-        self.fit_seconds = None  # device time of the last fit (CUDA events)
+        self._incremental = bool(incremental)
+        self._fit_Xu = self._fit_rhs = None  # what the device factorisation was built from (unit-box rows, rhs)
+        self.fit_seconds = None  # device time of the last fit / extension (CUDA events)
+        self.fit_kind = None     # "lu", "cholesky" or "extension"
 
     # ------------------------------------------------------------------ device state
     @property
@@ -68,6 +74,9 @@ class GpuRBFInterpolant(_Base):
             self._handle = _lib.Handle(self._device)
             if self._exact:
                 self._handle.set_option(_lib.OPT_EXACT_DIST, 1)
+            if not self._incremental:
+                self._handle.set_option(_lib.OPT_INCREMENTAL, 0)
+            self._fit_Xu = self._fit_rhs = None
         return self._handle
 
     def __getstate__(self):
@@ -75,6 +84,7 @@ class GpuRBFInterpolant(_Base):
         # (controller.py:97-123, surrogate_strategy.py:166-180): drop the device handle, refit on demand.
         state = self.__dict__.copy()
         state["_handle"] = None
+        state["_fit_Xu"] = state["_fit_rhs"] = None
         state["c"] = None
         state["updated"] = False
         return state
@@ -86,17 +96,32 @@ class GpuRBFInterpolant(_Base):
         """rbf.py:89-95."""
         super().reset()
         self.L = self.U = self.piv = self.c = None
+        self._fit_Xu = self._fit_rhs = None
 
     # ------------------------------------------------------------------ fit
     def _fit(self):
-        """Lazy fit (rbf.py:97-168): saddle-point assembly + pivoted LU + solves on the device."""
+        """Lazy fit (rbf.py:97-168).  First fit: assembly + factorisation + solves on the device (rbf.py:110-130).
+        Points added since the last fit: the resident factorisation is extended by their rows (rbf.py:132-161);
+        when the library declines -- nothing extendable resident, pre-allocated room or conditioning budget used up,
+        a non-positive pivot -- a full refit follows, as at rbf.py:149-153."""
         if self.updated:
             return
-        assert self.num_pts >= self.ntail  # rbf.py:111
+        n = self.num_pts
+        assert n >= self.ntail  # rbf.py:111
         rhs = self.output_transformation(self.fX.copy())  # rbf.py:164
-        c, secs = self.handle.fit(self._X[: self.num_pts], rhs, self._kid, self._tid, self.eta)
+        Xu = self._X[:n]
+        res = None
+        k = 0 if self._fit_Xu is None else self._fit_Xu.shape[0]
+        if self._incremental and 0 < k < n and np.array_equal(Xu[:k], self._fit_Xu):
+            rhs_changed = not np.array_equal(np.ravel(rhs)[:k], self._fit_rhs)
+            res = self.handle.extend(Xu, rhs, self._tid, rhs_changed)
+        if res is None:
+            res = self.handle.fit(Xu, rhs, self._kid, self._tid, self.eta)
+        c, secs = res
+        self._fit_Xu, self._fit_rhs = Xu.copy(), np.ravel(rhs).copy()
         self.c = c.reshape(-1, 1)
         self.fit_seconds = secs
+        self.fit_kind = self.handle.last_fit_method
         self.updated = True
 
     def set_coefficients(self, c):
@@ -105,6 +130,7 @@ class GpuRBFInterpolant(_Base):
         c = np.asarray(c, dtype=np.float64).reshape(-1, 1)
         assert c.shape[0] == self.num_pts + self.ntail
         self.handle.load_model(self._X[: self.num_pts], c, self._kid, self._tid)
+        self._fit_Xu = self._fit_rhs = None  # the resident factorisation (if any) no longer matches the model
         self.c = c
         self.updated = True
 
