@@ -15,12 +15,10 @@ void set_error(const char* fmt, ...) {
 
 int deriv_scratch_doubles(const b200rbf_ctx* h, long long m, size_t* out);
 int chol_fit_weights(b200rbf_ctx* h, const double* Xu_dev, const double* f_dev, int n, int d, int kernel, double eta,
-                     CholWork* wk, int* info_dev, int cap_rows);
-int chol_fit_tail(b200rbf_ctx* h, const CholWork& w, const double* f_dev, const double* g_dev, double eta,
-                  double* c_full_dev, int n_base, int n_all);
-int chol_extend_weights(b200rbf_ctx* h, const double* f_dev, int n, bool rhs_changed, int* info_dev);
-int ext_refresh_rhs(b200rbf_ctx* h, const double* f_dev);
-int trsv_sync_error(b200rbf_ctx* h, unsigned* err_host);
+                     CholWork* wk, int* info_dev, int cap_rows, double* c_out);
+int chol_fit_tail(b200rbf_ctx* h, const CholWork& w, double* c_full_dev, double* tailc_out, int n_rows);
+int chol_extend_weights(b200rbf_ctx* h, const double* f_dev, int n, bool rhs_changed, int* info_dev, double* c_out);
+int ensure_fit_sync(b200rbf_ctx* h);
 int run_generate(b200rbf_ctx* h, int kind, long long m, int d, const double* xbest, const double* lb, const double* ub,
                  const double* sigma, double prob_perturb, const int* subset, int nsub, const unsigned char* int_mask,
                  unsigned long long seed, double* cand_dev);
@@ -76,27 +74,32 @@ __global__ void pad_points_kernel(const double* __restrict__ src, int n, int d, 
   const int si = i < n ? i : n - 1;  // pad rows repeat the last point: no effect on a min, weight 0 in a sum
   dst[e] = k < d ? src[(size_t)si * d + k] : 0.0;
 }
-__global__ void split_coef_kernel(const double* __restrict__ c, int t, int n, double* __restrict__ coef, int npad,
-                                  double* __restrict__ tailc) {
+// The resident model in ONE launch (it was three): thread = padded center row i.
+//   centers[i]   (dpad)  the row, pad rows repeat the last point (no effect on a min, weight 0 in a sum), pad dims 0
+//   coef[i], tailc       the RBF weights (pad 0) and the tail coefficients, from c = [tail (t); weights (n)]
+//   xrows[i] (ds), cnorm[i], aug[i]   operands of score_mma_kernel: the row with stride ds, its squared norm, and the
+//                        augmented copy whose slots d and d + 1 carry 1 and |c|^2 (nullptr: not needed)
+__global__ void install_kernel(const double* __restrict__ src, const double* __restrict__ c, int n, int d, int t,
+                               double* __restrict__ centers, int npad, int dpad, double* __restrict__ coef,
+                               double* __restrict__ tailc, double* __restrict__ xrows, int ds,
+                               double* __restrict__ cnorm, double* __restrict__ aug) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < npad) coef[i] = i < n ? c[t + i] : 0.0;
   if (i < t) tailc[i] = c[i];
-}
-// centers with row stride ds and their squared norms (operands of score_mma_kernel)
-__global__ void mma_points_kernel(const double* __restrict__ src, int n, int d, double* __restrict__ dst, int npad,
-                                  int ds, double* __restrict__ cnorm, double* __restrict__ aug) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npad) return;
+  coef[i] = i < n ? c[t + i] : 0.0;
   const int si = i < n ? i : n - 1;
+  const double* row = src + (size_t)si * d;
+  for (int k = 0; k < dpad; ++k) centers[(size_t)i * dpad + k] = k < d ? row[k] : 0.0;
+  if (xrows == nullptr) return;
   double n2 = 0.0;
   for (int k = 0; k < ds; ++k) {
-    const double v = k < d ? src[(size_t)si * d + k] : 0.0;
-    dst[(size_t)i * ds + k] = v;
+    const double v = k < d ? row[k] : 0.0;
+    xrows[(size_t)i * ds + k] = v;
+    if (aug != nullptr) aug[(size_t)i * ds + k] = v;
     n2 = fma(v, v, n2);
   }
   cnorm[i] = n2;
-  if (aug != nullptr) {  // the augmented copy: slots d and d + 1 carry 1 and |c|^2
-    for (int k = 0; k < ds; ++k) aug[(size_t)i * ds + k] = dst[(size_t)i * ds + k];
+  if (aug != nullptr) {
     aug[(size_t)i * ds + d] = 1.0;
     aug[(size_t)i * ds + d + 1] = n2;
   }
@@ -136,28 +139,21 @@ int install_model(b200rbf_ctx* h, const double* Xu_dev, const double* c_dev, int
   B2_TRY(M.centers.reserve((size_t)M.npad * M.dpad * sizeof(double)));
   B2_TRY(M.coef.reserve((size_t)M.npad * sizeof(double)));
   B2_TRY(M.tailc.reserve((size_t)M.ntail * sizeof(double)));
-  const long long tot = (long long)M.npad * M.dpad;
-  pad_points_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(Xu_dev, n, d, M.centers.as<double>(), M.npad,
-                                                                          M.dpad);
-  h->launches++;
-  B2_CUDA(cudaGetLastError());
-  const int cnt = M.npad > M.ntail ? M.npad : M.ntail;
-  split_coef_kernel<<<(cnt + 255) / 256, 256, 0, h->stream>>>(c_dev, M.ntail, n, M.coef.as<double>(), M.npad,
-                                                              M.tailc.as<double>());
-  h->launches++;
-  B2_CUDA(cudaGetLastError());
-  if (M.dpad <= kMaxRegDim) {  // operands of the DMMA score kernel
+  const bool mma = M.dpad <= kMaxRegDim;  // operands of the DMMA score kernel
+  if (mma) {
     M.ds = mma_stride(d);
     B2_TRY(M.centers_x.reserve((size_t)M.npad * M.ds * sizeof(double)));
     B2_TRY(M.cnorm.reserve((size_t)M.npad * sizeof(double)));
     M.aug = (d % 4 == 1 || d % 4 == 2);  // two free slots in the last k-step of the DMMA kernel
     if (M.aug) B2_TRY(M.centers_m.reserve((size_t)M.npad * M.ds * sizeof(double)));
-    mma_points_kernel<<<(M.npad + 127) / 128, 128, 0, h->stream>>>(Xu_dev, n, d, M.centers_x.as<double>(), M.npad, M.ds,
-                                                                  M.cnorm.as<double>(),
-                                                                  M.aug ? M.centers_m.as<double>() : nullptr);
-    h->launches++;
-    B2_CUDA(cudaGetLastError());
   }
+  const int cnt = M.npad > M.ntail ? M.npad : M.ntail;
+  install_kernel<<<(cnt + 127) / 128, 128, 0, h->stream>>>(
+      Xu_dev, c_dev, n, d, M.ntail, M.centers.as<double>(), M.npad, M.dpad, M.coef.as<double>(), M.tailc.as<double>(),
+      mma ? M.centers_x.as<double>() : nullptr, M.ds, mma ? M.cnorm.as<double>() : nullptr,
+      (mma && M.aug) ? M.centers_m.as<double>() : nullptr);
+  h->launches++;
+  B2_CUDA(cudaGetLastError());
   M.loaded = true;
   h->score.valid = false;
   return 0;
@@ -546,42 +542,36 @@ int b200rbf_fit(b200rbf_handle h, const double* Xu, const double* rhs, int n, in
                        tp16 * tp16 * sizeof(double) <= (size_t)h->max_smem_optin;
   B2_CHECK(h->fit_method != 2 || chol_ok, B200RBF_EINVAL,
            "the Cholesky fit needs a cubic / TPS kernel with the linear tail, n >= 2 ntail + 32 and dim <= 159");
-  bool done = false;
+  bool done = false, installed = false;
   ExtState& E = h->fit.ext;
   E.valid = false;
   if (chol_ok && (h->fit_method == 2 || (h->fit_method == 0 && n >= 128))) {
-    B2_TRY(h->fit.piv.reserve(256));
-    int* info_dev = h->fit.piv.as<int>();
+    B2_TRY(ensure_fit_sync(h));
+    TrsvSync* sy = h->fit.sync.as<TrsvSync>();
+    int* info_dev = &sy->info;
     B2_CUDA(cudaMemsetAsync(info_dev, 0, sizeof(int), h->stream));
     CholWork wk;
     // room for b200rbf_extend to append points in place: twice the rows (at least 1024), for the sizes where a refit
     // per added point is what a strategy would otherwise pay (rbf.py:132-161)
     int cap = 0;
     if (h->incremental && n <= kExtMaxBase) cap = 2 * n < 1024 ? 1024 : ((2 * n + 127) / 128) * 128;
-    B2_TRY(chol_fit_weights(h, Xd, rd, n, d, kernel, eta, &wk, info_dev, cap));
-    // (Phi + eta I) c for the tail: evaluate the weights-only model at its own centers with the fused score kernel
-    B2_CUDA(cudaMemsetAsync(cd, 0, (size_t)t * sizeof(double), h->stream));
-    B2_CUDA(cudaMemcpyAsync(cd + t, wk.v2, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    B2_TRY(chol_fit_weights(h, Xd, rd, n, d, kernel, eta, &wk, info_dev, cap, cd));  // cd = [0_t; weights]
+    B2_TRY(chol_fit_tail(h, wk, cd, nullptr, n));  // cd = [lambda; weights]
     B2_TRY(install_model(h, Xd, cd, n, d, kernel, tail));
-    const int br = block_rows(h->model.dpad);
-    const int np = (n + br - 1) / br + 8;
-    B2_TRY(h->tmp_out.reserve(((size_t)4 * np + n + 16) * sizeof(double)));
-    double* parts = h->tmp_out.as<double>();
-    double* g = parts + (size_t)4 * np;
-    ScorePlan plan;
-    B2_TRY(score_rows(h, plan, Xd, 0, n, nullptr, g, nullptr, parts, np, 0, 0));
-    B2_TRY(chol_fit_tail(h, wk, rd, g, eta, cd, n, n));
     if (cap > 0) {
       B2_TRY(E.Xu.reserve((size_t)cap * d * sizeof(double)));
       B2_CUDA(cudaMemcpyAsync(E.Xu.p, Xd, (size_t)n * d * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     }
-    unsigned* sync_err = reinterpret_cast<unsigned*>(info_host + 1);
-    B2_TRY(trsv_sync_error(h, sync_err));
-    B2_CUDA(cudaMemcpyAsync(info_host, info_dev, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    B2_CUDA(cudaEventRecord(h->ev_t1, h->stream));
+    unsigned* flags_host = reinterpret_cast<unsigned*>(info_host + 2);  // {err, info}
+    B2_CUDA(cudaMemcpyAsync(flags_host, &sy->err, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+    if (c_out) B2_TRY(copy_out(h, c_out, cd, (size_t)N * sizeof(double)));
     B2_CUDA(cudaStreamSynchronize(h->stream));
-    B2_CHECK(*sync_err == 0, B200RBF_ECUDA, "triangular solve: a block waited too long for its predecessor");
+    B2_CHECK(flags_host[0] == 0, B200RBF_ECUDA, "triangular solve: a block waited too long for its predecessor");
+    *info_host = (int)flags_host[1];
     if (*info_host == 0) {
       done = true;
+      installed = true;
       h->last_fit_method = 2;
       if (cap > 0) {
         E.valid = true;
@@ -593,6 +583,7 @@ int b200rbf_fit(b200rbf_handle h, const double* Xu, const double* rhs, int n, in
         E.w = wk;
       }
     } else {
+      h->model.loaded = false;
       B2_CHECK(h->fit_method != 2, B200RBF_ESINGULAR,
                "Cholesky fit failed (%s step, index %d): projected matrix not numerically positive definite",
                *info_host < 0 ? "tail QR" : "factorisation", *info_host < 0 ? -*info_host : *info_host);
@@ -603,10 +594,12 @@ int b200rbf_fit(b200rbf_handle h, const double* Xu, const double* rhs, int n, in
     B2_TRY(run_fit(h, Xd, rd, n, d, kernel, tail, eta, cd, info_host));
     h->last_fit_method = 1;
   }
-  B2_TRY(install_model(h, Xd, cd, n, d, kernel, tail));
-  B2_CUDA(cudaEventRecord(h->ev_t1, h->stream));
-  if (c_out) B2_TRY(copy_out(h, c_out, cd, (size_t)N * sizeof(double)));
-  B2_CUDA(cudaStreamSynchronize(h->stream));
+  if (!installed) {
+    B2_TRY(install_model(h, Xd, cd, n, d, kernel, tail));
+    B2_CUDA(cudaEventRecord(h->ev_t1, h->stream));
+    if (c_out) B2_TRY(copy_out(h, c_out, cd, (size_t)N * sizeof(double)));
+    B2_CUDA(cudaStreamSynchronize(h->stream));
+  }
   if (fit_seconds) {
     float ms = 0.f;
     B2_CUDA(cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1));
@@ -644,28 +637,22 @@ int b200rbf_extend(b200rbf_handle h, const double* Xu, const double* rhs, int n,
   B2_TRY(copy_in(h, Xall + (size_t)n_old * d, Xu + (size_t)n_old * d, (size_t)(n - n_old) * d * sizeof(double)));
   B2_TRY(copy_in(h, rd, rhs, (size_t)n * sizeof(double)));
   B2_CUDA(cudaEventRecord(h->ev_t0, h->stream));
-  int* info_dev = h->fit.piv.as<int>();
+  B2_TRY(ensure_fit_sync(h));
+  TrsvSync* sy = h->fit.sync.as<TrsvSync>();
+  int* info_dev = &sy->info;
   B2_CUDA(cudaMemsetAsync(info_dev, 0, sizeof(int), h->stream));
   E.valid = false;  // until this extension has been checked
-  B2_TRY(chol_extend_weights(h, rd, n, rhs_changed != 0, info_dev));
-  // tail exactly as in the full fit, over the base points: lambda = R0^-1 Q0^T (f_0 - ((Phi + eta I) c)_0)
-  B2_CUDA(cudaMemsetAsync(cd, 0, (size_t)t * sizeof(double), h->stream));
-  B2_CUDA(cudaMemcpyAsync(cd + t, E.w.v2, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-  B2_TRY(install_model(h, Xall, cd, n, d, E.kernel, B200RBF_TAIL_LINEAR));
-  const int br = block_rows(h->model.dpad);
-  const int np = (E.n0 + br - 1) / br + 8;
-  B2_TRY(h->tmp_out.reserve(((size_t)4 * np + E.n0 + 16) * sizeof(double)));
-  double* parts = h->tmp_out.as<double>();
-  double* g = parts + (size_t)4 * np;
-  ScorePlan plan;
-  B2_TRY(score_rows(h, plan, Xall, 0, E.n0, nullptr, g, nullptr, parts, np, 0, 0));
-  B2_TRY(chol_fit_tail(h, E.w, rd, g, E.eta, cd, E.n0, n));
+  B2_TRY(chol_extend_weights(h, rd, n, rhs_changed != 0, info_dev, cd));  // cd = [0_t; weights]
+  // tail exactly as in the full fit: lambda = R0^-1 (Q0^T f_0 - Wx^T c)
+  B2_TRY(chol_fit_tail(h, E.w, cd, nullptr, n));
   B2_TRY(install_model(h, Xall, cd, n, d, E.kernel, B200RBF_TAIL_LINEAR));
   B2_CUDA(cudaEventRecord(h->ev_t1, h->stream));
+  unsigned* flags_host = reinterpret_cast<unsigned*>(info_host + 2);  // {err, info}
+  B2_CUDA(cudaMemcpyAsync(flags_host, &sy->err, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
   if (c_out) B2_TRY(copy_out(h, c_out, cd, (size_t)N * sizeof(double)));
-  B2_TRY(trsv_sync_error(h, sync_err));
-  B2_CUDA(cudaMemcpyAsync(info_host, info_dev, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   B2_CUDA(cudaStreamSynchronize(h->stream));
+  *info_host = (int)flags_host[1];
+  *sync_err = flags_host[0];
   if (fit_seconds) {
     float ms = 0.f;
     B2_CUDA(cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1));

@@ -175,7 +175,7 @@ struct ScoreState {
 // when the factorisation may be extended by fit_extend.cu)
 struct CholWork {
   double *P, *Qneg, *W, *Acat, *Bcat, *T21, *Linv, *LinvT, *Tn, *G, *R1, *R2, *R, *S, *gpart, *v0, *v1, *v2, *q;
-  double *Rinv, *fq, *bvec, *u, *mrow, *gbuf;  // extension state: R^-1, Q0^T f_0, T^T f, L^-1 T^T f, scratch rows
+  double *Rinv, *fq, *bvec, *u, *mrow, *gbuf, *part;  // extension state: R^-1, Q0^T f_0, T^T f, L^-1 T^T f, scratch
   int n, n16, t, tp, ld;
 };
 
@@ -184,7 +184,10 @@ constexpr int kExtMaxBase = 8192;    // largest point count whose factorisation 
 constexpr int kExtGrowth = 4;        // refit from scratch once the point count exceeds this multiple of the base
 constexpr int kTrsvMaxBlocks = 160;  // x 128 rows = 20 480
 struct TrsvSync {
-  unsigned ticket, done, err, pad;
+  unsigned ticket, done;
+  unsigned err;  // a block gave up waiting for its predecessor
+  int info;      // factorisation status: 0 ok, > 0 non-positive pivot near that row, < 0 tail QR failure
+
   unsigned flag[kTrsvMaxBlocks];
 };
 

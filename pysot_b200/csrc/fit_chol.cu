@@ -21,7 +21,7 @@
 //      the panel below it by one DMMA GEMM with the inverse) inside 512-column outer panels whose trailing update is
 //      one lower-triangle DMMA GEMM with K = 512
 //   6. c = Pi L^-T L^-1 Pi f   (strip GEMV + 128 x 128 matrix-vector products with the diagonal-block inverses)
-//   7. lambda from step 7 of the header formula; (Phi + eta I) c is evaluated by the fused score kernel (api.cu)
+//   7. lambda = R^-1 (Q^T f - W^T c): the projected residual needs W from step 3 only, no second pass over Phi
 #include "common.cuh"
 
 namespace b200rbf {
@@ -477,73 +477,6 @@ __global__ void finish_panel_kernel(const double* __restrict__ Tn, int rows, int
   }
 }
 
-// x[0 .. rows) = B y (transpose == 0) or B^T y (transpose != 0) for one kNB x kNB lower-triangular block B = L_bb^-1.
-// 512 threads: thread (o = tid & 127, part = tid >> 7) sums a quarter of output o's terms, the quarters meet in
-// shared memory.  The block is staged through shared memory so that both walks are conflict-free and every global
-// read is coalesced and issued up front.
-constexpr int kMvThreads = 512, kMvParts = kMvThreads / kNB;
-__global__ void __launch_bounds__(kMvThreads) block_matvec_kernel(const double* __restrict__ B, int rows,
-                                                                  const double* __restrict__ y, double* __restrict__ x,
-                                                                  int transpose) {
-  extern __shared__ double s[];  // kNB x (kNB + 1)
-  __shared__ double sy[kNB];
-  __shared__ double sp[kMvParts][kNB];
-  const int st = kNB + 1, tid = threadIdx.x, o = tid & (kNB - 1), part = tid >> 7;
-  if (tid < kNB) sy[tid] = tid < rows ? y[tid] : 0.0;
-  for (int i = part; i < rows; i += kMvParts) s[i * st + o] = B[(size_t)i * kNB + o];
-  __syncthreads();
-  double a0 = 0.0, a1 = 0.0;
-  if (o < rows) {
-    if (!transpose) {  // x[o] = sum_{k <= o} B[o][k] y[k]
-      int k = part;
-      for (; k + kMvParts <= o; k += 2 * kMvParts) {
-        a0 = fma(s[o * st + k], sy[k], a0);
-        a1 = fma(s[o * st + k + kMvParts], sy[k + kMvParts], a1);
-      }
-      if (k <= o) a0 = fma(s[o * st + k], sy[k], a0);
-    } else {  // x[o] = sum_{i >= o} B[i][o] y[i]
-      int i = o + part;
-      for (; i + kMvParts < rows; i += 2 * kMvParts) {
-        a0 = fma(s[i * st + o], sy[i], a0);
-        a1 = fma(s[(i + kMvParts) * st + o], sy[i + kMvParts], a1);
-      }
-      if (i < rows) a0 = fma(s[i * st + o], sy[i], a0);
-    }
-  }
-  sp[part][o] = a0 + a1;
-  __syncthreads();
-  if (tid < rows) x[tid] = (sp[0][tid] + sp[1][tid]) + (sp[2][tid] + sp[3][tid]);
-}
-
-// y[c] -= sum_{r in [r0, r0+rows)} A[r][c] x[r]  for c < ccount.  CTA = 32 columns x 8 row groups: coalesced over c,
-// each thread walks rows / 8 rows, the groups meet in shared memory.
-__global__ void __launch_bounds__(256) col_update_kernel(const double* __restrict__ A, int ld, int r0, int rows, int ccount,
-                                                         const double* __restrict__ x, double* __restrict__ y) {
-  __shared__ double sx[kNB];
-  __shared__ double sp[8][33];
-  const int tid = threadIdx.y * 32 + threadIdx.x;
-  if (tid < kNB) sx[tid] = tid < rows ? x[r0 + tid] : 0.0;
-  __syncthreads();
-  const int c = blockIdx.x * 32 + threadIdx.x;
-  double a0 = 0.0, a1 = 0.0;
-  if (c < ccount) {
-    int r = threadIdx.y;
-    for (; r + 8 < rows; r += 16) {
-      a0 = fma(A[(size_t)(r0 + r) * ld + c], sx[r], a0);
-      a1 = fma(A[(size_t)(r0 + r + 8) * ld + c], sx[r + 8], a1);
-    }
-    if (r < rows) a0 = fma(A[(size_t)(r0 + r) * ld + c], sx[r], a0);
-  }
-  sp[threadIdx.y][threadIdx.x] = a0 + a1;
-  __syncthreads();
-  if (threadIdx.y == 0 && c < ccount) {
-    double t = 0.0;
-#pragma unroll
-    for (int g = 0; g < 8; ++g) t += sp[g][threadIdx.x];
-    y[c] -= t;
-  }
-}
-
 // out[c] = sum_i Q[i][c] v[i]  (c < tp); one CTA of 1024 threads
 __global__ void __launch_bounds__(1024) qt_vec_kernel(const double* __restrict__ Q, int n, int tp,
                                                       const double* __restrict__ v, double* __restrict__ out) {
@@ -570,36 +503,24 @@ __global__ void sub_q_kernel(const double* __restrict__ Q, int n, int tp, const 
   for (int c = 0; c < tp; ++c) s = fma(Q[(size_t)i * tp + c], q[c], s);
   v[i] -= s;
 }
+// c_out[0 .. t) = 0 and c_out[t + i] = v[i] - sum_c Q[i][c] q[c] for i < n: the projected weights in the coefficient layout
+__global__ void project_out_kernel(const double* __restrict__ Q, int n, int tp, int t, const double* __restrict__ q,
+                                   const double* __restrict__ v, double* __restrict__ c_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < t) c_out[i] = 0.0;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int c = 0; c < tp; ++c) s = fma(Q[(size_t)i * tp + c], q[c], s);
+  c_out[t + i] = v[i] - s;
+}
 __global__ void copy_pad_kernel(const double* __restrict__ src, int n, double* __restrict__ dst, int npad) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < npad) dst[i] = i < n ? src[i] : 0.0;
-}
-// lambda = R^-1 q (R upper t x t, leading dimension tp), then c_full = [lambda; c]
-__global__ void tail_finish_kernel(const double* __restrict__ R, int tp, int t, const double* __restrict__ q,
-                                   const double* __restrict__ c, int n, double* __restrict__ c_full) {
-  extern __shared__ double lam[];
-  if (threadIdx.x == 0) {
-    for (int i = t - 1; i >= 0; --i) {
-      double v = q[i];
-      for (int k = i + 1; k < t; ++k) v = fma(-R[i * tp + k], lam[k], v);
-      lam[i] = v / R[i * tp + i];
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < t; i += blockDim.x) c_full[i] = lam[i];
-  for (int i = threadIdx.x; i < n; i += blockDim.x) c_full[t + i] = c[i];
 }
 __global__ void neg_kernel(const double* __restrict__ a, double* __restrict__ b, long long n) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e < n) b[e] = -a[e];
 }
-// r[i] = f[i] - (g[i] + eta c[i])
-__global__ void residual_kernel(const double* __restrict__ f, const double* __restrict__ g,
-                                const double* __restrict__ c, double eta, int n, double* __restrict__ r) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) r[i] = f[i] - fma(eta, c[i], g[i]);
-}
-
 int gram(b200rbf_ctx* h, const double* X, const double* Y, int n, int tp, double* partial, double* G) {
   const int nparts = (n + 63) / 64;
   const size_t smem = 2 * 64 * (size_t)tp * sizeof(double);
@@ -613,11 +534,11 @@ int gram(b200rbf_ctx* h, const double* X, const double* Y, int n, int tp, double
 
 }  // namespace
 
-// c_rbf (n) <- RBF weights; keeps Q, R in the workspace for the tail step.  info_dev: 0 ok, != 0 -> fall back to LU.
+// c_out (t + n) <- [0; RBF weights]; keeps Q, R in the workspace for the tail step.  info_dev: 0 ok, != 0 -> fall back to LU.
 // cap_rows > n: the factor, Q / W, the diagonal-block inverses and the vectors are laid out for cap_rows rows so that
 // fit_extend.cu can append points to this factorisation in place (no regrowth, no copies).
 int chol_fit_weights(b200rbf_ctx* h, const double* Xu_dev, const double* f_dev, int n, int d, int kernel, double eta,
-                     CholWork* wk, int* info_dev, int cap_rows) {
+                     CholWork* wk, int* info_dev, int cap_rows, double* c_out) {
   FitState& F = h->fit;
   const int t = d + 1, tp = (t + 15) & ~15, n16 = (n + 31) & ~31;  // n16: padded to the 32-column sub-blocks
   const int rcap = cap_rows > n16 ? ((cap_rows + kNB - 1) / kNB) * kNB : n16, ld = rcap;
@@ -632,6 +553,7 @@ int chol_fit_weights(b200rbf_ctx* h, const double* Xu_dev, const double* f_dev, 
   const size_t oLi = take((size_t)((rcap + kNB - 1) / kNB) * kNB * kNB), oLiT = take((size_t)kNB * kNB);
   const size_t oTn = take((size_t)n16 * kNB);
   const size_t oRi = take((size_t)tp * tp), oFq = take(tp), oBv = take(rcap), oU = take(rcap), oMr = take(rcap), oGb = take(rcap);
+  const size_t oPt = take((size_t)(rcap / 256 + 2) * 2 * tp);
   B2_TRY(F.chol.reserve(need * sizeof(double)));
   B2_TRY(F.A.reserve(((size_t)rcap * ld + 1024) * sizeof(double)));
   double* base = F.chol.as<double>();
@@ -639,7 +561,7 @@ int chol_fit_weights(b200rbf_ctx* h, const double* Xu_dev, const double* f_dev, 
   w.P = base + oP; w.Qneg = base + oQn; w.W = base + oW; w.Acat = base + oAc; w.Bcat = base + oBc; w.T21 = base + oT21;
   w.G = base + oG; w.R1 = base + oR1; w.R2 = base + oR2; w.R = base + oR; w.S = base + oS;
   w.Linv = base + oLi; w.LinvT = base + oLiT; w.Tn = base + oTn; w.gpart = base + oGp; w.v0 = base + oV0; w.v1 = base + oV1; w.v2 = base + oV2; w.q = base + oq;
-  w.Rinv = base + oRi; w.fq = base + oFq; w.bvec = base + oBv; w.u = base + oU; w.mrow = base + oMr; w.gbuf = base + oGb;
+  w.Rinv = base + oRi; w.fq = base + oFq; w.bvec = base + oBv; w.u = base + oU; w.mrow = base + oMr; w.gbuf = base + oGb; w.part = base + oPt;
   w.n = n; w.n16 = n16; w.t = t; w.tp = tp; w.ld = ld;
   double* A = F.A.as<double>();
   double* Q = w.P;  // P is orthonormalised in place
@@ -739,21 +661,57 @@ int chol_fit_weights(b200rbf_ctx* h, const double* Xu_dev, const double* f_dev, 
   B2_TRY(trsv_pipelined(h, A, ld, w.Linv, n, w.u, w.v2, true));
   qt_vec_kernel<<<1, 1024, 0, h->stream>>>(Q, n, tp, w.v2, w.q);
   LAUNCHED(h);
-  sub_q_kernel<<<(n16 + 255) / 256, 256, 0, h->stream>>>(Q, n, tp, w.q, w.v2, n16);
+  project_out_kernel<<<((n > t ? n : t) + 255) / 256, 256, 0, h->stream>>>(Q, n, tp, t, w.q, w.v2, c_out);
   LAUNCHED(h);
   if (cap_rows > 0) B2_TRY(ext_make_rinv(h, w));
-  return 0;  // RBF weights in w.v2[0 .. n)
+  return 0;  // RBF weights in c_out[t .. t + n), c_out[0 .. t) = 0
 }
 
 // lambda and the final coefficient vector: g = Phi c (without eta) evaluated by the caller
-// n_base: the points P = Q R was factored for (rows of Q); n_all >= n_base: all points carrying a weight in w.v2
-int chol_fit_tail(b200rbf_ctx* h, const CholWork& w, const double* f_dev, const double* g_dev, double eta,
-                  double* c_full_dev, int n_base, int n_all) {
-  residual_kernel<<<(n_base + 255) / 256, 256, 0, h->stream>>>(f_dev, g_dev, w.v2, eta, n_base, w.v0);
-  LAUNCHED(h);
-  qt_vec_kernel<<<1, 1024, 0, h->stream>>>(w.P, n_base, w.tp, w.v0, w.q);
-  LAUNCHED(h);
-  tail_finish_kernel<<<1, 256, (size_t)w.tp * sizeof(double), h->stream>>>(w.R, w.tp, w.t, w.q, w.v2, n_all, c_full_dev);
+// Tail coefficients in ONE single-CTA launch:  lambda = R^-1 Q0^T (f_0 - ((Phi + eta I) c)_0).  Because
+// Q0^T (Phi + eta I)_{0,:} = W^T with W = [(Phi00 + eta I) Q0 ; rows Q0^T phi(X0, x_i) of the appended points] -- kept by
+// the fit (step 3) and the extension -- the projected residual is  Q0^T f_0 - W^T c = fq - W^T c:  an n x t reduction
+// instead of re-evaluating the n x n kernel matrix (the first version ran the fused score kernel over all centers for
+// this).  Then a column-oriented back substitution with one barrier per unknown (t <= 160).
+// c_full = [lambda; c] where c already sits at c_full + t;  tailc_out (optional): the resident model's tail.
+__global__ void __launch_bounds__(1024) tail_fused_kernel(const double* __restrict__ fq, const double* __restrict__ W,
+                                                          int n_rows, int tp, int t, const double* __restrict__ R,
+                                                          double* c_full, double* tailc_out) {
+  __shared__ double red[1024];
+  extern __shared__ double lam[];  // tp values + tp right-hand side
+  double* v = lam + tp;
+  const double* c = c_full + t;
+  const int tid = threadIdx.x;
+  {
+    const int a = tid % tp, groups = 1024 / tp, gr = tid / tp;
+    double s = 0.0;
+    if (gr < groups)
+      for (int i = gr; i < n_rows; i += groups) s = fma(W[(size_t)i * tp + a], c[i], s);
+    red[tid] = (gr < groups) ? s : 0.0;
+    __syncthreads();
+    if (tid < tp) {
+      double tot = 0.0;
+      for (int q = 0; q < groups; ++q) tot += red[q * tp + tid];
+      v[tid] = fq[tid] - tot;
+    }
+    __syncthreads();
+  }
+  for (int i = t - 1; i >= 0; --i) {
+    if (tid == 0) lam[i] = v[i] / R[i * tp + i];
+    __syncthreads();
+    if (tid < i) v[tid] = fma(-R[tid * tp + i], lam[i], v[tid]);
+    __syncthreads();
+  }
+  for (int i = tid; i < t; i += 1024) {
+    c_full[i] = lam[i];
+    if (tailc_out != nullptr) tailc_out[i] = lam[i];
+  }
+}
+
+// n_rows: all points carrying a weight (rows of W); c_full_dev + t holds their weights
+int chol_fit_tail(b200rbf_ctx* h, const CholWork& w, double* c_full_dev, double* tailc_out, int n_rows) {
+  tail_fused_kernel<<<1, 1024, 2 * (size_t)w.tp * sizeof(double), h->stream>>>(w.fq, w.W, n_rows, w.tp, w.t, w.R, c_full_dev,
+                                                                              tailc_out);
   LAUNCHED(h);
   return 0;
 }

@@ -196,69 +196,122 @@ __device__ void cta_qt_vec(const double* __restrict__ Q, int n, int tp, const do
   __syncthreads();
 }
 
-// Everything that precedes the triangular solve for new point j = N (its coordinates are already in Xu row N):
-//   qt = Rinv^T p_j -> Qx[N];  col = phi(|u_i - u_j|) (+ eta at i = N);  w = Q0^T col[0:n0] -> Wx[N];
-//   g = col - Wx qt;  s = Q0^T g[0:n0];  mrow[i] = g[i] - Qx[i].s  (i <= N);  bvec[N] = f_N - qt.fq
-// One CTA: the phases are reductions over the base points separated by barriers; `gbuf` is global scratch (cap doubles).
-constexpr int kExtThreads = 1024;
-__global__ void __launch_bounds__(kExtThreads) extend_row_kernel(const double* __restrict__ Xu, int d, int n0, int N,
-                                                                 int kern, double eta, const double* __restrict__ Rinv,
-                                                                 int t, int tp, double* Qx, double* Wx,
-                                                                 const double* __restrict__ fq, const double* __restrict__ f,
-                                                                 double* gbuf, double* __restrict__ mrow,
-                                                                 double* __restrict__ bvec, int exact) {
+// Everything that precedes the triangular solve for new point j = N (its coordinates are already in Xu row N), in two
+// row-parallel launches (the first version was one 1024-thread CTA walking all rows five times: 60 us at N = 1000):
+//   A:  qt = Rinv^T p_j -> Qx[N];  col_i = phi(|u_i - u_j|) (+ eta at i = N);  g_i = col_i - Wx[i].qt (i < N);
+//       per-CTA partial sums over the base rows of  Q0^T col  (-> w = Wx[N])  and  Q0^T g  (-> s)
+//   B:  w, s from the partials (fixed order: deterministic);  g_N = col_N - w.qt;  mrow[i] = g_i - Qx[i].s (i <= N);
+//       Wx[N] = w;  bvec[N] = f_N - qt.fq
+constexpr int kExtRows = 256;     // rows (= threads) per CTA of the row-parallel passes
+constexpr int kExtThreads = 1024;  // the single-CTA reductions
+__global__ void __launch_bounds__(kExtRows) ext_row_a_kernel(const double* __restrict__ Xu, int d, int n0, int N, int kern,
+                                                             double eta, const double* __restrict__ Rinv, int t, int tp,
+                                                             double* Qx, const double* __restrict__ Wx, double* gbuf,
+                                                             double* __restrict__ part, int exact) {
   extern __shared__ double sh[];
-  double* red = sh;                   // kExtThreads
-  double* p = red + kExtThreads;      // tp
-  double* qt = p + tp;                // tp
-  double* wv = qt + tp;               // tp
-  double* sv = wv + tp;               // tp
-  double* uj = sv + tp;               // d
+  double* uj = sh;             // d
+  double* p = uj + d;          // tp
+  double* qt = p + tp;         // tp
+  double* scol = qt + tp;      // kExtRows
+  double* sg = scol + kExtRows;  // kExtRows
   const int tid = threadIdx.x;
-  for (int k = tid; k < d; k += kExtThreads) uj[k] = Xu[(size_t)N * d + k];
+  for (int k = tid; k < d; k += kExtRows) uj[k] = Xu[(size_t)N * d + k];
   __syncthreads();
-  if (tid < tp) p[tid] = tid == 0 ? 1.0 : (tid < t ? uj[tid - 1] : 0.0);
+  for (int a = tid; a < tp; a += kExtRows) p[a] = a == 0 ? 1.0 : (a < t ? uj[a - 1] : 0.0);
   __syncthreads();
-  if (tid < tp) {  // qt_a = sum_{k <= a} Rinv[k][a] p_k   (R0^T qt = p)
+  for (int a = tid; a < tp; a += kExtRows) {  // qt_a = sum_{k <= a} Rinv[k][a] p_k   (R0^T qt = p)
     double s = 0.0;
-    if (tid < t)
-      for (int k = 0; k <= tid; ++k) s = fma(Rinv[k * tp + tid], p[k], s);
-    qt[tid] = s;
-    Qx[(size_t)N * tp + tid] = s;
+    if (a < t)
+      for (int k = 0; k <= a; ++k) s = fma(Rinv[k * tp + a], p[k], s);
+    qt[a] = s;
   }
-  for (int i = tid; i <= N; i += kExtThreads) {
+  __syncthreads();
+  const int i = blockIdx.x * kExtRows + tid;
+  double col = 0.0, g = 0.0;
+  if (i <= N) {
     const double* ui = Xu + (size_t)i * d;
     double r2 = 0.0;
     for (int k = 0; k < d; ++k) {
       const double df = ui[k] - uj[k];
       r2 = exact ? __dadd_rn(r2, __dmul_rn(df, df)) : fma(df, df, r2);
     }
-    double v = ext_phi_r2(kern, r2);
-    if (i == N) v += eta;
-    gbuf[i] = v;
+    col = ext_phi_r2(kern, r2);
+    if (i == N) {
+      col += eta;
+      g = col;  // w.qt is subtracted in pass B
+      for (int a = 0; a < tp; ++a) Qx[(size_t)N * tp + a] = qt[a];
+    } else {
+      const double* wr = Wx + (size_t)i * tp;
+      double s = 0.0;
+      for (int a = 0; a < t; ++a) s = fma(wr[a], qt[a], s);
+      g = col - s;
+    }
+    gbuf[i] = g;
+  }
+  const bool base = i < n0;
+  scol[tid] = base ? col : 0.0;
+  sg[tid] = base ? g : 0.0;
+  __syncthreads();
+  const int r0 = blockIdx.x * kExtRows;
+  if (r0 < n0) {
+    const int rows = min(kExtRows, n0 - r0);
+    for (int a = tid; a < tp; a += kExtRows) {
+      double sw = 0.0, ss = 0.0;
+      for (int r = 0; r < rows; ++r) {
+        const double q = Qx[(size_t)(r0 + r) * tp + a];
+        sw = fma(q, scol[r], sw);
+        ss = fma(q, sg[r], ss);
+      }
+      part[((size_t)blockIdx.x * 2 + 0) * tp + a] = sw;
+      part[((size_t)blockIdx.x * 2 + 1) * tp + a] = ss;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kExtRows) ext_row_b_kernel(int n0, int N, int t, int tp, const double* Qx, double* Wx,
+                                                             const double* __restrict__ part,
+                                                             const double* __restrict__ fq, const double* __restrict__ f,
+                                                             const double* gbuf, double* __restrict__ mrow,
+                                                             double* __restrict__ bvec) {
+  extern __shared__ double sh[];
+  double* w = sh;        // tp
+  double* sv = w + tp;   // tp
+  double* qt = sv + tp;  // tp
+  __shared__ double s_wq;
+  const int tid = threadIdx.x;
+  const int nbase = (n0 + kExtRows - 1) / kExtRows;  // CTAs of pass A that held base rows
+  for (int a = tid; a < tp; a += kExtRows) {
+    double sw = 0.0, ss = 0.0;
+    for (int b = 0; b < nbase; ++b) {
+      sw += part[((size_t)b * 2 + 0) * tp + a];
+      ss += part[((size_t)b * 2 + 1) * tp + a];
+    }
+    w[a] = sw;
+    sv[a] = ss;
+    qt[a] = Qx[(size_t)N * tp + a];
   }
   __syncthreads();
-  cta_qt_vec(Qx, n0, tp, gbuf, wv, red);  // rows < n0 of Qx are Q0
-  if (tid < tp) Wx[(size_t)N * tp + tid] = wv[tid];
-  __syncthreads();
-  for (int i = tid; i <= N; i += kExtThreads) {
-    const double* wr = Wx + (size_t)i * tp;
+  if (tid == 0) {
     double s = 0.0;
-    for (int a = 0; a < t; ++a) s = fma(wr[a], qt[a], s);
-    gbuf[i] -= s;
+    for (int a = 0; a < t; ++a) s = fma(w[a], qt[a], s);
+    s_wq = s;
   }
   __syncthreads();
-  cta_qt_vec(Qx, n0, tp, gbuf, sv, red);
-  for (int i = tid; i <= N; i += kExtThreads) {
+  const int i = blockIdx.x * kExtRows + tid;
+  if (i <= N) {
     const double* qr = Qx + (size_t)i * tp;
     double s = 0.0;
     for (int a = 0; a < t; ++a) s = fma(qr[a], sv[a], s);
-    mrow[i] = gbuf[i] - s;
+    const double g = gbuf[i] - (i == N ? s_wq : 0.0);
+    mrow[i] = g - s;
   }
-  if (tid == 0) {
-    double s = 0.0;
-    for (int a = 0; a < t; ++a) s = fma(qt[a], fq[a], s);
-    bvec[N] = f[N] - s;
+  if (blockIdx.x == (unsigned)(N / kExtRows)) {  // the CTA that owns row N
+    for (int a = tid; a < tp; a += kExtRows) Wx[(size_t)N * tp + a] = w[a];
+    if (tid == 0) {
+      double s = 0.0;
+      for (int a = 0; a < t; ++a) s = fma(qt[a], fq[a], s);
+      bvec[N] = f[N] - s;
+    }
   }
 }
 
@@ -333,14 +386,17 @@ __global__ void rinv_kernel(const double* __restrict__ R, int tp, int t, double*
   }
 }
 
-// c[i] = y[i] - (i < n0 ? Q0[i].v : 0),  v = Qx^T y  (N rows);  one CTA computes v, then the elementwise pass
+// c_out[t + i] = y[i] - (i < n0 ? Q0[i].v : 0),  v = Qx^T y  (N rows), c_out[0 .. t) = 0;  one CTA computes v, then the
+// elementwise pass
 __global__ void __launch_bounds__(kExtThreads) ext_weights_kernel(const double* __restrict__ Qx, int n0, int N, int t,
                                                                   int tp, const double* __restrict__ y,
-                                                                  double* __restrict__ c) {
+                                                                  double* __restrict__ c_out) {
   extern __shared__ double sh[];
   double* red = sh;
   double* v = red + kExtThreads;
+  double* c = c_out + t;
   cta_qt_vec(Qx, N, tp, y, v, red);
+  if (threadIdx.x < t) c_out[threadIdx.x] = 0.0;
   for (int i = threadIdx.x; i < N; i += kExtThreads) {
     double s = 0.0;
     if (i < n0) {
@@ -370,13 +426,20 @@ __global__ void __launch_bounds__(kExtThreads) ext_rhs_kernel(const double* __re
 
 }  // namespace
 
-int trsv_pipelined(b200rbf_ctx* h, const double* L, int ld, const double* Linv, int N, const double* b, double* x,
-                   bool transpose) {
+// the flags of the pipelined solves; its `info` word doubles as the factorisation status of fit_chol.cu / this file
+int ensure_fit_sync(b200rbf_ctx* h) {
   FitState& F = h->fit;
   if (F.sync.p == nullptr) {
     B2_TRY(F.sync.reserve(sizeof(TrsvSync)));
     B2_CUDA(cudaMemsetAsync(F.sync.p, 0, sizeof(TrsvSync), h->stream));
   }
+  return 0;
+}
+
+int trsv_pipelined(b200rbf_ctx* h, const double* L, int ld, const double* Linv, int N, const double* b, double* x,
+                   bool transpose) {
+  FitState& F = h->fit;
+  B2_TRY(ensure_fit_sync(h));
   const int nblk = (N + kTB - 1) / kTB;
   B2_CHECK(nblk >= 1 && nblk <= kTrsvMaxBlocks, B200RBF_EINVAL, "triangular solve: %d rows out of range", N);
   static DeviceOnce attr;
@@ -414,22 +477,21 @@ int ext_refresh_rhs(b200rbf_ctx* h, const double* f_dev) {
 }
 
 // append points [E.N, n) (their unit-box rows are already in E.Xu, values f_dev) to the resident factorisation and solve for the
-// RBF weights of all n points -> w.v2[0 .. n).  info_dev != 0 afterwards: a pivot failed, the state is invalid.
-int chol_extend_weights(b200rbf_ctx* h, const double* f_dev, int n, bool rhs_changed, int* info_dev) {
+// RBF weights of all n points -> c_out = [0_t; weights].  info_dev != 0 afterwards: a pivot failed, the state is invalid.
+int chol_extend_weights(b200rbf_ctx* h, const double* f_dev, int n, bool rhs_changed, int* info_dev, double* c_out) {
   ExtState& E = h->fit.ext;
   const CholWork& w = E.w;
   double* A = h->fit.A.as<double>();
   const int d = E.d;
-  static DeviceOnce attr;
-  if (attr.pending(h->device)) {
-    B2_CUDA(cudaFuncSetAttribute(extend_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ext_smem(256, 192)));
-    attr.done(h->device);
-  }
   if (rhs_changed) B2_TRY(ext_refresh_rhs(h, f_dev));
   for (int j = E.N; j < n; ++j) {
-    extend_row_kernel<<<1, kExtThreads, ext_smem(w.tp, d), h->stream>>>(E.Xu.as<double>(), d, E.n0, j, E.kernel, E.eta, w.Rinv,
-                                                                        w.t, w.tp, w.P, w.W, w.fq, f_dev, w.gbuf, w.mrow,
-                                                                        w.bvec, h->exact_dist ? 1 : 0);
+    const int ctas = (j + 1 + kExtRows - 1) / kExtRows;
+    const size_t sm_a = ((size_t)d + 2 * (size_t)w.tp + 2 * kExtRows) * sizeof(double), sm_b = 3 * (size_t)w.tp * sizeof(double);
+    ext_row_a_kernel<<<ctas, kExtRows, sm_a, h->stream>>>(E.Xu.as<double>(), d, E.n0, j, E.kernel, E.eta, w.Rinv, w.t, w.tp, w.P,
+                                                          w.W, w.gbuf, w.part, h->exact_dist ? 1 : 0);
+    LAUNCHED(h);
+    ext_row_b_kernel<<<ctas, kExtRows, sm_b, h->stream>>>(E.n0, j, w.t, w.tp, w.P, w.W, w.part, w.fq, f_dev, w.gbuf, w.mrow,
+                                                          w.bvec);
     LAUNCHED(h);
     B2_TRY(trsv_pipelined(h, A, w.ld, w.Linv, j, w.mrow, A + (size_t)j * w.ld, false));
     finish_row_kernel<<<1, 512, 0, h->stream>>>(A, w.ld, j, w.mrow, w.bvec, w.u, w.Linv, info_dev);
@@ -437,15 +499,8 @@ int chol_extend_weights(b200rbf_ctx* h, const double* f_dev, int n, bool rhs_cha
   }
   E.N = n;
   B2_TRY(trsv_pipelined(h, A, w.ld, w.Linv, n, w.u, w.v1, true));
-  ext_weights_kernel<<<1, kExtThreads, ext_smem(w.tp, 0), h->stream>>>(w.P, E.n0, n, w.t, w.tp, w.v1, w.v2);
+  ext_weights_kernel<<<1, kExtThreads, ext_smem(w.tp, 0), h->stream>>>(w.P, E.n0, n, w.t, w.tp, w.v1, c_out);
   LAUNCHED(h);
-  return 0;
-}
-
-int trsv_sync_error(b200rbf_ctx* h, unsigned* err_host) {
-  *err_host = 0;
-  if (h->fit.sync.p == nullptr) return 0;
-  B2_CUDA(cudaMemcpyAsync(err_host, &h->fit.sync.as<TrsvSync>()->err, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
   return 0;
 }
 
