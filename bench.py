@@ -12,10 +12,16 @@ NCCL moves only statistics, (merit, index) pairs and the winning row).
 
 metric   candidate x center pairs / s, whole job
 value    device-resident candidates (inputs in HBM before the timed region), CUDA events, max over ranks
-e2e      the public API call with HOST (pinned) candidate arrays: H2D of the batch and D2H of the picks inside
+e2e      the public API call with HOST (pinned) candidate arrays: H2D of the batch and D2H of the picks inside;
+         `e2e_pageable` is the same call with a plain (pageable) numpy array, what a pySOT caller hands over
 roofline the fused score kernel against the FP64 FMA pipe, measured live (the path is FP64-compute-bound, see
-         DESIGN.md): achieved = pairs * (3d + 6) flops / kernel time; the HBM figure is reported beside it
-fit      BASELINE's second headline number: RBF fit seconds at N = 20 000 (TPS, d = 10), rank 0 only
+         DESIGN.md): achieved = pairs * (3d + 6) flops / kernel time; the HBM figure is reported beside it;
+         `rooflines` adds predict and predict_deriv (config #3 shape, device tensors, CUDA events)
+parity   (N = 1) the GPU path against the oracle on the CPU baseline's own sample of the workload, outside the timed region
+sweep    config #4's candidate counts: 2^20 .. 2^26 candidates in total (split over the ranks), and one strong-scaling
+         point at 2^24 in total; candidates drawn on the device by b200rbf_generate
+fit      BASELINE's second headline number: RBF fit seconds at N = 20 000 (TPS, d = 10), rank 0 only, beside the
+         reference's CPU fit (oracle port, all host cores) at N = 1 000 / 5 000 / 20 000 (`cpu_baseline_fit`)
 
 --impl reference times the CPU restatement of the reference (oracle/, same scipy/numpy routines as pySOT) on a
 bounded sample of the same workload with every host core.
@@ -38,6 +44,13 @@ WEIGHTS = [0.3, 0.5, 0.8, 0.95]
 DTOL = 1e-3
 FLOPS_PER_PAIR = 3 * D + 6  # sub + fma per coordinate, sqrt, phi (2), weight fma (2), running min
 WORKLOAD = "config#4 candidate acquisition: d=50, n=20000 centers, cubic+linear tail, 2^20 DYCORS candidates per GPU, num_pts=4"
+
+
+def config_dict(world):
+    """Identical in both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "global_candidates": M_PER_GPU * world, "centers": N_CENTERS, "dim": D,
+            "num_pts": NUM_PTS, "parallelism": "candidate rows sharded x%d, centers replicated" % world,
+            "l2": "inputs larger than L2 (419 MB of candidates per GPU per step)"}
 
 
 def make_centers():
@@ -132,7 +145,7 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline
-def cpu_scoring_baseline(X, fX, Xpend, coef, xbest, budget_s=15.0, threads=None):
+def cpu_scoring_baseline(X, fX, Xpend, coef, xbest, budget_s=15.0, threads=None, keep=False):
     """The oracle port (same scipy cdist / numpy ufunc / dot calls as pySOT) on a bounded sample, all host threads."""
     from oracle import rbf_oracle as orc
 
@@ -150,11 +163,43 @@ def cpu_scoring_baseline(X, fX, Xpend, coef, xbest, budget_s=15.0, threads=None)
     cand = dycors_candidates_host(m, xbest, 12)
     t0 = time.perf_counter()
     fv, dm = orc.score_tiled(o, X, cand, Xpend, chunk=chunk, threads=threads)
-    orc.select_from_scores(cand, fv, dm, WEIGHTS, NUM_PTS, DTOL)
+    picked = orc.select_from_scores(cand, fv, dm, WEIGHTS, NUM_PTS, DTOL)
     dt = time.perf_counter() - t0
-    return {"value": m * N_CENTERS / dt, "unit": "pairs/s", "cores": threads, "kind": "port",
-            "sample": "%d candidates x %d centers, d=%d, tiled reference path (%d-row chunks on a %d-thread pool), "
-                      "%.1f s" % (m, N_CENTERS, D, chunk, threads, dt), "seconds": dt, "m": m}
+    out = {"value": m * N_CENTERS / dt, "unit": "pairs/s", "cores": threads, "kind": "port",
+           "sample": "%d candidates x %d centers, d=%d, tiled reference path (%d-row chunks on a %d-thread pool), "
+                     "%.1f s" % (m, N_CENTERS, D, chunk, threads, dt), "seconds": dt, "m": m}
+    if keep:
+        out["_sample"] = (cand, fv.ravel(), dm.ravel(), picked)
+    return out
+
+
+def cpu_fit_baseline(sizes=(1000, 5000, 20000)):
+    """The reference's _fit (rbf.py:110-130, 164-168: cdist, lu_factor, two solve_triangular) through the oracle port on
+    BASELINE config #3's inputs, all host cores (OpenBLAS threads), one cold run per size."""
+    from oracle import rbf_oracle as orc
+
+    out = []
+    for n in sizes:
+        need_gb = 5.0 * 8.0 * (n + 11) ** 2 / 1e9  # dists, Phi, A, LU copy, L / U copies of the reference
+        try:
+            import psutil
+
+            if psutil.virtual_memory().available / 1e9 < need_gb + 4.0:
+                out.append({"n": n, "skipped": "needs ~%.0f GB of host memory" % need_gb})
+                continue
+        except Exception:
+            pass
+        rng = np.random.default_rng(0)
+        X = rng.random((n, 10))
+        fX = (np.sin(3.0 * X.sum(axis=1)) + X[:, 0] ** 2)[:, None]
+        o = orc.OracleRBF(10, np.zeros(10), np.ones(10), "tps", "linear")
+        o.add_points(X, fX)
+        t0 = time.perf_counter()
+        o.fit()
+        out.append({"n": n, "d": 10, "kernel": "tps", "seconds": time.perf_counter() - t0, "cores": os.cpu_count(),
+                    "kind": "port"})
+        del o
+    return out
 
 
 def run_reference(args, rank):
@@ -179,7 +224,9 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "candidate x center pairs/s", "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / len(vals), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU reference path; each step is a bounded sample of the workload"},
+        "config": config_dict(max(1, args.gpus)),
+        "note": "CPU reference path (oracle port of pySOT's numpy / scipy calls, tiled over all host cores); each step is a "
+                "bounded sample of the workload",
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -187,9 +234,12 @@ def run_reference(args, rank):
 
 
 # ------------------------------------------------------------------------------------------------ native arm
-def fit_benchmark(pb, sizes=(1000, 5000, 20000)):
-    """BASELINE config #3: TPS + linear tail, d = 10, X ~ U[0,1]^10 seed 0, fX = sin(3 sum X) + X0^2."""
-    out = []
+def fit_benchmark(pb, peaks, sizes=(1000, 5000, 20000)):
+    """BASELINE config #3: TPS + linear tail, d = 10, X ~ U[0,1]^10 seed 0, fX = sin(3 sum X) + X0^2.  Returns the fit
+    records and the roofline entries of predict / predict_deriv (device tensors in and out, CUDA events)."""
+    import torch
+
+    out, roofs = [], []
     for n in sizes:
         rng = np.random.default_rng(0)
         X = rng.random((n, 10))
@@ -204,14 +254,18 @@ def fit_benchmark(pb, sizes=(1000, 5000, 20000)):
             best_wall = min(best_wall, time.perf_counter() - t0)
             best_dev = min(best_dev, s.fit_seconds)
         N = n + 11
-        # algorithmic work of the REFERENCE's algorithm (LU of the saddle-point system); the null-space
-        # Cholesky does half of it, so "tflops" below is an equivalent rate, comparable across solvers
+        # algorithmic work of the REFERENCE's algorithm (LU of the saddle-point system).  The null-space
+        # Cholesky executes n^3 / 3 + the rank-3t update and W = Phi Q (2 n^2 * 5 tp) + assembly instead.
         flops = 2.0 / 3.0 * N ** 3 + 2.0 * N ** 2 + 0.5 * n * n * (3 * 10 + 4)
+        executed = n ** 3 / 3.0 + 2.0 * n * n * 5 * 16 + 0.5 * n * n * (3 * 10 + 4) + 4.0 * n * n
         resid = float(np.max(np.abs(s.predict(X[:2000]) + s.eta * s.c[11:11 + min(n, 2000)] - fX[:2000])))
         rec = {"n": n, "d": 10, "kernel": "tps", "solver": s.handle.last_fit_method, "seconds_device": best_dev,
-               "seconds_host_to_host": best_wall, "tflops": flops / best_dev / 1e12, "interp_residual": resid}
+               "seconds_host_to_host": best_wall, "tflops": flops / best_dev / 1e12,
+               "frac_of_dmma_peak": flops / best_dev / 1e12 / peaks["dmma_tflops"],
+               "tflops_executed": executed / best_dev / 1e12,
+               "frac_executed": executed / best_dev / 1e12 / peaks["dmma_tflops"], "interp_residual": resid}
         if n == sizes[-1]:
-            # config #3's other half: predict on 1e5 points (seed 1), and predict_deriv, host arrays in and out
+            # config #3's other half: predict on 1e5 points (seed 1), and predict_deriv, host arrays in and out ...
             q = np.random.default_rng(1).random((100000, 10))
             s.predict(q)  # untimed: sizes the staging buffers
             t0 = time.perf_counter()
@@ -221,9 +275,35 @@ def fit_benchmark(pb, sizes=(1000, 5000, 20000)):
             t0 = time.perf_counter()
             s.predict_deriv(q)
             rec["predict_deriv_pairs_per_s"] = q.shape[0] * n / (time.perf_counter() - t0)
+            # ... and device-resident: the kernels alone against the FP64 datapath (3d + 6 / 5d + 6 flops)
+            dev = torch.device("cuda", s._device)
+            m2 = 1 << 20
+            qd = torch.rand((m2, 10), dtype=torch.float64, device=dev)
+            od = torch.empty(m2, dtype=torch.float64, device=dev)
+            gd = torch.empty((m2, 10), dtype=torch.float64, device=dev)
+            stream = torch.cuda.current_stream(dev)
+            s.handle.set_stream(stream.cuda_stream)
+            try:
+                for name, fn, fl in (("predict", lambda: s.handle.predict(qd, s.lb, s.ub, out=od, m=m2), 3 * 10 + 6),
+                                     ("predict_deriv", lambda: s.handle.predict_deriv(qd, s.lb, s.ub, out=gd, m=m2), 5 * 10 + 6)):
+                    fn()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(stream)
+                    for _ in range(3):
+                        fn()
+                    e1.record(stream)
+                    torch.cuda.synchronize(dev)
+                    ms = e0.elapsed_time(e1) / 3
+                    tf = float(m2) * n * fl / (ms * 1e-3) / 1e12
+                    roofs.append({"kernel": "%s (TPS, d=10, n=%d, m=2^20 device-resident)" % (name, n), "bound": "tensor",
+                                  "achieved": tf, "peak": peaks["dfma_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["dfma_tflops"],
+                                  "flops_per_pair": fl, "launch_ms": ms, "pairs_per_s": float(m2) * n / (ms * 1e-3)})
+            finally:
+                s.handle.set_stream(None)
+            del qd, od, gd
         out.append(rec)
         del s
-    return out
+    return out, roofs
 
 
 def run_native(args, rank, world, local_rank):
@@ -261,12 +341,20 @@ def run_native(args, rank, world, local_rank):
     rbf = pb.GpuRBFInterpolant(dim=D, lb=lb, ub=ub, device=local_rank)  # Cubic + LinearTail (reference default)
     rbf.add_points(X, fX)
     t0 = time.perf_counter()
-    rbf._fit()  # every rank fits its own replica (the fit does not shard: "replicas only")
-    fit50 = {"n": N_CENTERS, "d": D, "kernel": "cubic", "solver": rbf.handle.last_fit_method,
-             "seconds_device": rbf.fit_seconds,
-             "seconds_host_to_host": time.perf_counter() - t0,
-             "note": "cold: the first fit of the process, it allocates the 3.4 GB workspace inside the timed region; "
-                     "the warm figures are in `fit`"}
+    fit50 = None
+    if rank == 0:  # ONE fit (it does not shard: "replicas only"); the replicas receive the coefficients
+        rbf._fit()
+        fit50 = {"n": N_CENTERS, "d": D, "kernel": "cubic", "solver": rbf.handle.last_fit_method,
+                 "seconds_device": rbf.fit_seconds,
+                 "seconds_host_to_host": time.perf_counter() - t0,
+                 "note": "cold: the first fit of the process, it allocates the 3.4 GB workspace inside the timed region; "
+                         "the warm figures are in `fit`"}
+    if world > 1:
+        cvec = torch.from_numpy(rbf.c.ravel().copy() if rank == 0 else np.empty(N_CENTERS + D + 1)).to(device)
+        dist.broadcast(cvec, src=0)
+        if rank != 0:
+            rbf.set_coefficients(cvec.cpu().numpy())  # b200rbf_load
+        del cvec
     h = rbf.handle
     Xdist = np.vstack((X, Xpend))
 
@@ -278,10 +366,10 @@ def run_native(args, rank, world, local_rank):
     backend = GpuShardBackend(rbf)
 
     def step_device():
-        return sharded_select(backend, cand_dev, Xdist, True, WEIGHTS, NUM_PTS, DTOL)
+        return sharded_select(backend, cand_dev, Xdist, True, WEIGHTS, NUM_PTS, DTOL, offset=rank * M_PER_GPU)
 
     def step_e2e():
-        return sharded_weighted_distance_merit(NUM_PTS, rbf, X, fX, cand_host, WEIGHTS, Xpend, DTOL)
+        return sharded_weighted_distance_merit(NUM_PTS, rbf, X, fX, cand_host, WEIGHTS, Xpend, DTOL, offset=rank * M_PER_GPU)
 
     # ---- value: device-resident inputs, CUDA events on the stream the kernels run on (torch's current stream)
     for _ in range(args.warmup):
@@ -318,6 +406,58 @@ def run_native(args, rank, world, local_rank):
     e2e_value = pairs_per_step * args.steps / e2e_s
     h2d = M_PER_GPU * D * 8 + 7 * D * 8 + 2 * D * 8
     d2h = NUM_PTS * (16 + D * 8) + 4 * 8
+
+    # ---- the same call with a PAGEABLE numpy array (what a pySOT caller hands over): staged through the handle's
+    # pinned double buffer chunk by chunk
+    cand_pageable = np.array(cand_host, copy=True)
+    sharded_weighted_distance_merit(NUM_PTS, rbf, X, fX, cand_pageable, WEIGHTS, Xpend, DTOL, offset=rank * M_PER_GPU)
+    barrier()
+    t0 = time.perf_counter()
+    pg_steps = max(1, min(args.steps, 3))
+    for _ in range(pg_steps):
+        pts_pg, idx_pg = sharded_weighted_distance_merit(NUM_PTS, rbf, X, fX, cand_pageable, WEIGHTS, Xpend, DTOL, offset=rank * M_PER_GPU)
+    barrier()
+    pg_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_pageable = {"value": pairs_per_step * pg_steps / pg_s, "unit": "pairs/s", "ms_per_step": 1e3 * pg_s / pg_steps,
+                    "steps": pg_steps, "same_picks_as_pinned": bool(np.array_equal(idx_pg, idx))}
+    del cand_pageable
+
+    # ---- config #4's candidate counts (total over the ranks), candidates drawn on the device by b200rbf_generate
+    import types
+
+    _Prob = types.SimpleNamespace(dim=D, lb=lb, ub=ub, int_var=np.array([], dtype=int))
+
+    def timed_device_steps(cand_t, steps):
+        off = rank * int(cand_t.shape[0])
+        sharded_select(backend, cand_t, Xdist, True, WEIGHTS, NUM_PTS, DTOL, offset=off)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            sharded_select(backend, cand_t, Xdist, True, WEIGHTS, NUM_PTS, DTOL, offset=off)
+        b.record()
+        barrier()
+        return max_over_ranks(a.elapsed_time(b)) / steps
+
+    sweep, strong = [], None
+    if not args.skip_extras:
+        del cand_dev
+        torch.cuda.empty_cache()
+        for log2m in (20, 22, 24, 26):
+            m_tot = 1 << log2m
+            m_loc = m_tot // world
+            c_t = pb.generate_on_device("dycors", _Prob, rbf, X, fX, prob_perturb=0.4, sampling_radius=0.2, num_cand=m_loc,
+                                        seed=1000 + 17 * log2m + rank)
+            ms = timed_device_steps(c_t, 2 if log2m <= 24 else 1)
+            rec = {"global_candidates": m_tot, "per_gpu": m_loc, "ms_per_step": ms,
+                   "value": float(m_tot) * N_CENTERS / (ms * 1e-3), "unit": "pairs/s"}
+            sweep.append(rec)
+            if log2m == 24:
+                strong = {"global_candidates": m_tot, "n_gpus": world, "ms_per_step": ms, "value": rec["value"],
+                          "unit": "pairs/s", "scaling": "strong",
+                          "note": "fixed global candidate count split over the ranks; compare across --gpus runs"}
+            del c_t
+            torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
@@ -358,22 +498,37 @@ def run_native(args, rank, world, local_rank):
         "metric": "candidate x center pairs/s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_candidates": M_PER_GPU * world, "centers": N_CENTERS, "dim": D,
-                   "num_pts": NUM_PTS, "parallelism": "candidate rows sharded x%d, centers replicated" % world,
-                   "l2": "inputs larger than L2 (419 MB of candidates per GPU per step)"},
+        "config": config_dict(world),
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": 1e3 * e2e_s / args.steps},
+                "ms_per_step": 1e3 * e2e_s / args.steps, "host_memory": "pinned"},
+        "e2e_pageable": e2e_pageable, "sweep": sweep, "strong_scaling": strong,
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "picked": [int(i) for i in picks[0]],
         "fit_d50": fit50,
     }
     if world == 1 and not args.skip_extras:
         coef = rbf.c.ravel().copy()
-        line["cpu_baseline"] = {k: v for k, v in cpu_scoring_baseline(X, fX, Xpend, coef, xbest).items()
-                                if k in ("value", "unit", "cores", "kind", "sample")}
-        fits = fit_benchmark(pb)
-        for f in fits:
-            f["frac_of_dmma_peak"] = f["tflops"] / peaks["dmma_tflops"]
+        cb = cpu_scoring_baseline(X, fX, Xpend, coef, xbest, keep=True)
+        line["cpu_baseline"] = {k: v for k, v in cb.items() if k in ("value", "unit", "cores", "kind", "sample")}
+        # parity on the CPU baseline's own sample (same coefficients: the GPU's real fit), default DMMA kernel
+        c_s, fv_o, dm_o, pick_o = cb["_sample"]
+        idx_g, _, fv_g, dm_g, _ = pb.merit_select_indices(NUM_PTS, rbf, X, c_s, WEIGHTS, Xpend, DTOL, want_scores=True)
+        line["parity"] = {
+            "sample": "%d candidates x %d centers (the cpu_baseline sample), coefficients from the GPU fit" % (len(fv_o), N_CENTERS),
+            "fvals_relmax": float(np.max(np.abs(fv_g - fv_o)) / np.max(np.abs(fv_o))),
+            "dmerit_relmax": float(np.max(np.abs(dm_g - dm_o)) / np.max(np.abs(dm_o))),
+            "picks_gpu": [int(i) for i in idx_g], "picks_oracle": [int(i) for i in pick_o],
+            "picks_identical": bool(np.array_equal(idx_g, pick_o)),
+            "bars": "fvals 1e-10, dmerit 1e-12, picks identical (north_star); golden-vector versions of this check at "
+                    "2^17 candidates and for the N = 5 000 / 20 000 fits: tests/test_gpu_large_shapes.py"}
+        del cb
+        fits, roofs = fit_benchmark(pb, peaks)
         line["fit"] = fits
+        line["rooflines"] = [dict(roofline, name="score (headline)")] + roofs
+        line["cpu_baseline_fit"] = cpu_fit_baseline()
+        for f, c in zip(line["fit"], line["cpu_baseline_fit"]):
+            if "seconds" in c:
+                f["cpu_seconds"] = c["seconds"]
+                f["speedup_vs_cpu"] = c["seconds"] / f["seconds_host_to_host"]
     print(json.dumps(line))
     if world > 1:
         dist.barrier()

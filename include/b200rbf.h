@@ -159,6 +159,18 @@ int b200rbf_shard_stats(b200rbf_handle h, double* stats_dev);
 /* local merit + argmin using the (globally reduced) stats_dev; writes pair_dev; index = local + idx_offset */
 int b200rbf_shard_argmin(b200rbf_handle h, double w, double dtol, const double* stats_dev, long long idx_offset,
                          void* pair_dev);
+/* Device-side min-loc (no host round trip between the picks; what pysot_b200/sharded.py uses):
+ *   best_dev   : 2 + d doubles {merit, int64 global index (raw bits), the candidate row behind it} -> all-gather
+ *   gathered   : world x (2 + d) doubles, the ranks' best_dev records in rank order
+ * shard_best  = local merit + argmin with the (globally reduced) stats_dev, writes best_dev.
+ * shard_apply = picks the winner among the gathered records (lowest merit, then lowest global index, NaN first: np.argmin),
+ *               copies the winning record to result_dev (2 + d doubles), marks the row taken on its owner
+ *               (fvals[jj] = inf, candidate_srbf.py:50) and, when update != 0, folds the winner into dmerit
+ *               (candidate_srbf.py:54-55) and writes this rank's new {fmin, -fmax, dmin, -dmax} to stats_dev. */
+int b200rbf_shard_best(b200rbf_handle h, double w, double dtol, const double* stats_dev, long long idx_offset,
+                       double* best_dev);
+int b200rbf_shard_apply(b200rbf_handle h, const double* gathered_dev, int world, long long idx_offset, int update,
+                        double* result_dev, double* stats_dev);
 /* copy resident candidate row local_idx into winner_dev and mark fvals[local_idx] = inf (owner only) */
 int b200rbf_shard_take(b200rbf_handle h, long long local_idx, double* winner_dev);
 /* dmerit = minimum(dmerit, || cand - winner ||) on the local shard; refreshes the local dmin / dmax */

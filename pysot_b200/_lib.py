@@ -38,6 +38,8 @@ PROTOTYPES = {
                                    C.c_ulonglong, _vp]),
     "b200rbf_shard_stats": (C.c_int, [_vp, _vp]),
     "b200rbf_shard_argmin": (C.c_int, [_vp, C.c_double, C.c_double, _vp, C.c_longlong, _vp]),
+    "b200rbf_shard_best": (C.c_int, [_vp, C.c_double, C.c_double, _vp, C.c_longlong, _vp]),
+    "b200rbf_shard_apply": (C.c_int, [_vp, _vp, C.c_int, C.c_longlong, C.c_int, _vp, _vp]),
     "b200rbf_shard_take": (C.c_int, [_vp, C.c_longlong, _vp]),
     "b200rbf_shard_update": (C.c_int, [_vp, _vp]),
     "b200rbf_fp64_peaks": (C.c_int, [_vp, C.c_double, _vp]),
@@ -237,6 +239,13 @@ class Handle:
 
     def shard_argmin(self, w, dtol, stats_dev, idx_offset, pair_dev):
         check(load().b200rbf_shard_argmin(self._h, float(w), float(dtol), ptr(stats_dev), int(idx_offset), ptr(pair_dev)))
+
+    def shard_best(self, w, dtol, stats_dev, idx_offset, best_dev):
+        check(load().b200rbf_shard_best(self._h, float(w), float(dtol), ptr(stats_dev), int(idx_offset), ptr(best_dev)))
+
+    def shard_apply(self, gathered_dev, world, idx_offset, update, result_dev, stats_dev):
+        check(load().b200rbf_shard_apply(self._h, ptr(gathered_dev), int(world), int(idx_offset), 1 if update else 0,
+                                         ptr(result_dev), ptr(stats_dev)))
 
     def shard_take(self, local_idx, winner_dev):
         check(load().b200rbf_shard_take(self._h, int(local_idx), ptr(winner_dev)))

@@ -83,6 +83,9 @@ def merit_select_indices(num_pts, surrogate, X, cand, weights, Xpend=None, dtol=
     # Under the strategies the surrogate's points are exactly X (surrogate_strategy.py:427-429); then one
     # distance serves both metrics.  extra_points (surrogate_strategy.py:243-247) break the aliasing.
     alias = X.shape == surrogate.X.shape and np.array_equal(X, surrogate.X)
+    group = getattr(surrogate, "device_group", None)
+    if group is not None and not _is_cuda_tensor(cand) and not want_scores:  # one process, several devices
+        return group.select(num_pts, X, cand, weights, Xpend, dtol)
     h = surrogate.handle
     with _torch_stream(h, cand):
         fv, dm, st = h.score(cand, surrogate.lb, surrogate.ub, Xdist, alias, want_scores=want_scores, m=cand.shape[0])

@@ -864,6 +864,42 @@ int b200rbf_shard_argmin(b200rbf_handle h, double w, double dtol, const double* 
   return 0;
 }
 
+int b200rbf_shard_best(b200rbf_handle h, double w, double dtol, const double* stats_dev, long long idx_offset,
+                       double* best_dev) {
+  B2_CHECK(h && stats_dev && best_dev, B200RBF_EINVAL, "NULL argument");
+  B2_CHECK(h->score.valid, B200RBF_ESTATE, "nothing scored: call b200rbf_score first");
+  B2_CUDA(cudaSetDevice(h->device));
+  ScoreState& S = h->score;
+  int nb = 0;
+  B2_TRY(launch_merit_argmin(h, S.fvals.as<double>(), S.dmerit.as<double>(), S.m, stats_dev, 1, w, dtol, idx_offset,
+                             S.pair_parts.p, &nb));
+  B2_TRY(launch_best(h, S.pair_parts.p, nb, S.cand, S.d, idx_offset, best_dev));
+  return 0;
+}
+
+int b200rbf_shard_apply(b200rbf_handle h, const double* gathered_dev, int world, long long idx_offset, int update,
+                        double* result_dev, double* stats_dev) {
+  B2_CHECK(h && gathered_dev && result_dev, B200RBF_EINVAL, "NULL argument");
+  B2_CHECK(world >= 1, B200RBF_EINVAL, "world must be >= 1");
+  B2_CHECK(!update || stats_dev, B200RBF_EINVAL, "stats_dev is required with update");
+  B2_CHECK(h->score.valid, B200RBF_ESTATE, "nothing scored: call b200rbf_score first");
+  B2_CUDA(cudaSetDevice(h->device));
+  ScoreState& S = h->score;
+  const Model& M = h->model;
+  B2_TRY(launch_decide(h, gathered_dev, world, S.d, idx_offset, S.m, S.fvals.as<double>(), S.winner.as<double>(), M.dpad,
+                       result_dev));
+  if (update) {
+    int cnt = 0;
+    B2_TRY(launch_update(h, S.cand, S.m, S.d, S.winner.as<double>(), S.dmerit.as<double>(), S.parts.as<double>(), S.nparts,
+                         &cnt, h->exact_dist));
+    B2_TRY(launch_stats(h, S.parts.as<double>(), S.nparts, cnt, 2, S.stats.as<double>()));
+    negate_stats_kernel<<<1, 32, 0, h->stream>>>(S.stats.as<double>(), stats_dev);
+    h->launches++;
+    B2_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
 int b200rbf_shard_take(b200rbf_handle h, long long local_idx, double* winner_dev) {
   B2_CHECK(h && winner_dev, B200RBF_EINVAL, "NULL argument");
   B2_CHECK(h->score.valid, B200RBF_ESTATE, "nothing scored: call b200rbf_score first");

@@ -280,6 +280,10 @@ int launch_merit_argmin(b200rbf_ctx* h, const double* fvals, const double* dmeri
                         int stats_negated, double w, double dtol, long long idx_off, void* pair_parts, int* nblocks);
 int launch_pick(b200rbf_ctx* h, const void* pair_parts, int nparts, const double* cand, int d, double* fvals,
                 double* winner, int dpad, void* result_slot, void* pair_out);
+int launch_best(b200rbf_ctx* h, const void* pair_parts, int nparts, const double* cand, int d, long long idx_off,
+                double* best_out);
+int launch_decide(b200rbf_ctx* h, const double* gathered, int world, int d, long long idx_off, long long m, double* fvals,
+                  double* winner, int dpad, double* result);
 int launch_take(b200rbf_ctx* h, const double* cand, int d, long long idx, double* fvals, double* winner, int dpad);
 int launch_update(b200rbf_ctx* h, const double* cand, long long m, int d, const double* winner, double* dmerit,
                   double* parts, int stride, int* count_out, bool exact);

@@ -165,6 +165,55 @@ __global__ void __launch_bounds__(kSelThreads) pick_kernel(const Pair* __restric
   }
 }
 
+// ---- sharded path, device-side min-loc (no host round trip between the picks) ----
+// single CTA: this rank's best pair and the candidate row behind it -> best = {merit, int64 index bits, row[d]}
+__global__ void __launch_bounds__(kSelThreads) best_kernel(const Pair* __restrict__ parts, int nparts,
+                                                           const double* __restrict__ cand, int d, long long idx_off,
+                                                           double* __restrict__ best_out) {
+  __shared__ Pair s_pairs[kSelThreads / 32];
+  Pair best{d_inf(), 0x7fffffffffffffffLL};
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) {
+    Pair p = parts[i];
+    if (better(p.v, p.i, best.v, best.i)) best = p;
+  }
+  best = block_argmin(best, s_pairs);
+  if (threadIdx.x == 0) {
+    best_out[0] = best.v;
+    best_out[1] = __longlong_as_double(best.i);
+  }
+  const long long local = best.i - idx_off;
+  for (int k = threadIdx.x; k < d; k += blockDim.x) best_out[2 + k] = cand[local * (long long)d + k];
+}
+
+// single CTA: the winner among the ranks' {merit, index, row} records (np.argmin order: NaN, value, lowest global
+// index); result = the winning record, winner = its row padded to dpad; the owner marks the row taken
+// (fvals[jj] = inf, candidate_srbf.py:50).  A rank with no candidates contributes index = LLONG_MAX.
+__global__ void __launch_bounds__(kSelThreads) decide_kernel(const double* __restrict__ gathered, int world, int d,
+                                                             long long idx_off, long long m, double* __restrict__ fvals,
+                                                             double* __restrict__ winner, int dpad,
+                                                             double* __restrict__ result) {
+  __shared__ int s_win;
+  if (threadIdx.x == 0) {
+    int bw = 0;
+    Pair best{gathered[0], __double_as_longlong(gathered[1])};
+    for (int r = 1; r < world; ++r) {
+      const double* rec = gathered + (size_t)r * (2 + d);
+      const Pair p{rec[0], __double_as_longlong(rec[1])};
+      if (better(p.v, p.i, best.v, best.i)) {
+        best = p;
+        bw = r;
+      }
+    }
+    s_win = bw;
+    const long long local = best.i - idx_off;
+    if (local >= 0 && local < m) fvals[local] = d_inf();
+  }
+  __syncthreads();
+  const double* rec = gathered + (size_t)s_win * (2 + d);
+  for (int k = threadIdx.x; k < 2 + d; k += blockDim.x) result[k] = rec[k];
+  for (int k = threadIdx.x; k < dpad; k += blockDim.x) winner[k] = k < d ? rec[2 + k] : 0.0;
+}
+
 __global__ void take_kernel(const double* __restrict__ cand, int d, long long idx, double* __restrict__ fvals,
                             double* __restrict__ winner, int dpad) {
   if (threadIdx.x == 0) fvals[idx] = d_inf();
@@ -260,6 +309,22 @@ int launch_pick(b200rbf_ctx* h, const void* pair_parts, int nparts, const double
   pick_kernel<<<1, kSelThreads, 0, h->stream>>>(reinterpret_cast<const Pair*>(pair_parts), nparts, cand, d, fvals,
                                                 winner, dpad, reinterpret_cast<Pair*>(result_slot),
                                                 reinterpret_cast<Pair*>(pair_out));
+  h->launches++;
+  B2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_best(b200rbf_ctx* h, const void* pair_parts, int nparts, const double* cand, int d, long long idx_off,
+                double* best_out) {
+  best_kernel<<<1, kSelThreads, 0, h->stream>>>(reinterpret_cast<const Pair*>(pair_parts), nparts, cand, d, idx_off, best_out);
+  h->launches++;
+  B2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_decide(b200rbf_ctx* h, const double* gathered, int world, int d, long long idx_off, long long m, double* fvals,
+                  double* winner, int dpad, double* result) {
+  decide_kernel<<<1, kSelThreads, 0, h->stream>>>(gathered, world, d, idx_off, m, fvals, winner, dpad, result);
   h->launches++;
   B2_CUDA(cudaGetLastError());
   return 0;

@@ -28,6 +28,9 @@ class GpuRBFInterpolant(_Base):
     :param device: CUDA ordinal (default: LOCAL_RANK or 0)
     :param exact_dist: accumulate squared distances with separate multiply and add exactly like
         scipy's cdist instead of fused multiply-add (bit-identical distances, ~2.5x slower scoring)
+    :param devices: list of CUDA ordinals; with more than one, ``weighted_distance_merit`` / ``candidate_*`` shard the
+        candidate rows over those devices from this one process (``pysot_b200/multi.py``); the fit, ``predict`` and
+        ``predict_deriv`` run on the first
     :param incremental: extend the resident factorisation when points are added (rbf.py:132-161) instead of
         refitting from scratch; False = every ``_fit`` is a fresh fit
 
@@ -38,7 +41,7 @@ class GpuRBFInterpolant(_Base):
     """
 
     def __init__(self, dim, lb, ub, output_transformation=None, kernel=None, tail=None, eta=1e-6, device=None,
-                 exact_dist=False, incremental=True):
+                 exact_dist=False, incremental=True, devices=None):
         if HAVE_PYSOT:
             super().__init__(dim=dim, lb=lb, ub=ub, output_transformation=output_transformation, kernel=kernel,
                              tail=tail, eta=eta)
@@ -58,7 +61,11 @@ class GpuRBFInterpolant(_Base):
             assert self.dim == self.tail.dim
         self._kid = kernel_id(self.kernel)
         self._tid = tail_id(self.tail)
+        if devices is not None and len(devices) > 0:
+            device = devices[0] if device is None else device
         self._device = default_device() if device is None else int(device)
+        self._devices = [int(v) for v in devices] if devices is not None and len(devices) > 1 else None
+        self._group = None
         self._exact = bool(exact_dist)
         self._handle = None
         self._incremental = bool(incremental)
@@ -79,11 +86,23 @@ class GpuRBFInterpolant(_Base):
             self._fit_Xu = self._fit_rhs = None
         return self._handle
 
+    @property
+    def device_group(self):
+        """The replicas on ``devices`` (None with a single device)."""
+        if self._devices is None:
+            return None
+        if self._group is None:
+            from .multi import DeviceGroup
+
+            self._group = DeviceGroup(self, self._devices)
+        return self._group
+
     def __getstate__(self):
         # CheckpointController dill-dumps the strategy, surrogate included, after every evaluation
         # (controller.py:97-123, surrogate_strategy.py:166-180): drop the device handle, refit on demand.
         state = self.__dict__.copy()
         state["_handle"] = None
+        state["_group"] = None
         state["_fit_Xu"] = state["_fit_rhs"] = None
         state["c"] = None
         state["updated"] = False

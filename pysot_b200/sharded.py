@@ -5,9 +5,10 @@ argmin, so each rank scores a contiguous block of candidate rows against its rep
 coefficients, and the ranks exchange only
 
   * ``{fmin, -fmax, dmin, -dmax}``   one all-reduce(MIN) after scoring, and ``{dmin, -dmax}`` again per extra pick
-  * ``(merit, global index)`` pairs   one all-gather per pick; lowest merit wins, lowest index on ties
-                                      (np.argmin's first-minimum rule, candidate_srbf.py:49)
-  * the winning candidate row          one broadcast of d doubles from its owner per extra pick
+  * ``{merit, global index, row}``    one all-gather per pick of every rank's local best and the candidate row
+                                      behind it (2 + d doubles); each rank then finds the winner on its own device:
+                                      lowest merit, lowest index on ties (np.argmin's first-minimum rule,
+                                      candidate_srbf.py:49) -- no broadcast, no host round trip between the picks
 
 No candidate data ever crosses NVLink.  The driver below is written against a small backend interface so the
 host logic is testable on CPU with gloo; ``GpuShardBackend`` is the product backend (C ABI phase calls).
@@ -16,7 +17,8 @@ import numpy as np
 
 
 class GpuShardBackend:
-    """Phase calls of include/b200rbf.h on this rank's handle; all buffers are CUDA tensors."""
+    """Phase calls of include/b200rbf.h on this rank's handle; all buffers are CUDA tensors, nothing is read back
+    between the picks."""
 
     def __init__(self, surrogate):
         import torch
@@ -25,42 +27,67 @@ class GpuShardBackend:
         self.s = surrogate
         self.h = surrogate.handle
         self.device = torch.device("cuda", surrogate._device)
+        self.m = 0
 
     def new(self, n, dtype):
         return self.torch.zeros(n, dtype=dtype, device=self.device)
 
     def score(self, cand, Xdist, alias):
+        """Fused scoring of the local rows; returns this rank's {fmin, -fmax, dmin, -dmax} (all +inf for an empty shard:
+        the neutral element of the MIN all-reduce)."""
         t = self.torch
+        self.m = int(cand.shape[0])
+        if self.m == 0:
+            return t.full((4,), float("inf"), dtype=t.float64, device=self.device)
         self.h.set_stream(t.cuda.current_stream(self.device).cuda_stream)
         if isinstance(cand, np.ndarray):
-            self.m = cand.shape[0]
             self.h.score(cand, self.s.lb, self.s.ub, Xdist, alias)
         else:  # CUDA tensor hand-off
             assert cand.is_cuda and cand.dtype == t.float64 and cand.is_contiguous()
-            self.m = cand.shape[0]
             self.h.score(cand, self.s.lb, self.s.ub, Xdist, alias, m=self.m)
         stats = self.new(4, t.float64)
         self.h.shard_stats(stats)
         return stats
 
-    def argmin(self, w, dtol, stats, offset):
-        pair = self.new(2, self.torch.float64)  # {merit, int64 index} as raw 8-byte words
-        self.h.shard_argmin(w, dtol, stats, offset, pair)
-        return pair
+    def best(self, w, dtol, stats, offset):
+        """{merit, global index (int64 bits), row[d]} of the local argmin; an empty shard never wins."""
+        t = self.torch
+        rec = self.new(2 + self.s.dim, t.float64)
+        if self.m == 0:
+            rec[0] = float("inf")
+            rec[1:2].view(t.int64)[0] = _INT64_MAX
+            return rec
+        self.h.shard_best(w, dtol, stats, offset, rec)
+        return rec
 
-    def take(self, local_idx):
-        row = self.new(self.s.dim, self.torch.float64)
-        self.h.shard_take(local_idx, row)
-        return row
-
-    def update(self, row):
-        self.h.shard_update(row)
-        stats = self.new(4, self.torch.float64)
-        self.h.shard_stats(stats)
+    def apply(self, gathered, world, offset, update, result):
+        """Winner of the gathered records -> result; mark it taken / fold it into dmerit locally; returns the new local
+        {fmin, -fmax, dmin, -dmax} when ``update``."""
+        t = self.torch
+        if self.m == 0:
+            result.copy_(_winner_record(t, gathered.view(world, -1)))
+            return t.full((4,), float("inf"), dtype=t.float64, device=self.device) if update else None
+        stats = self.new(4, t.float64) if update else None
+        self.h.shard_apply(gathered, world, offset, update, result, stats)
         return stats
 
     def finish(self):
-        self.h.set_stream(None)
+        if self.m > 0:
+            self.h.set_stream(None)
+
+
+_INT64_MAX = 0x7FFFFFFFFFFFFFFF
+
+
+def _winner_record(torch, rec):
+    """np.argmin order over records [merit, index bits, ...]: a NaN wins, then the smaller merit, then the smaller index
+    (tensor ops only: used by a rank that holds no candidates and by the CPU test backend)."""
+    merit = rec[:, 0]
+    idx = rec[:, 1].contiguous().view(torch.int64)
+    key = torch.where(torch.isnan(merit), torch.full_like(merit, -float("inf")), merit)
+    tie = key == key.min()
+    r = torch.argmin(torch.where(tie, idx, torch.full_like(idx, _INT64_MAX)))
+    return rec[r]
 
 
 def _better(av, ai, bv, bi):
@@ -73,68 +100,71 @@ def _better(av, ai, bv, bi):
     return ai < bi
 
 
-def sharded_select(backend, cand_local, Xdist, alias, weights, num_pts, dtol=1e-3, group=None):
+def shard_offset(m_local, backend, group=None):
+    """First global row index of this rank's block: ranks own contiguous blocks in rank order, so
+    global index = offset + local index and the lowest-index tie rule stays global.  One all-gather of the row counts
+    (and one host read); callers with equal or otherwise known blocks pass the offset to ``sharded_select`` instead."""
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return 0
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    counts = torch.zeros(world, dtype=torch.int64, device=backend.device)
+    counts[rank] = m_local
+    dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+    return int(counts[:rank].sum().item())
+
+
+def sharded_select(backend, cand_local, Xdist, alias, weights, num_pts, dtol=1e-3, group=None, offset=None):
     """Run the selection loop over all ranks' shards.  Every rank returns the same
-    ``(global_indices [num_pts], rows [num_pts, d])``; rows are None on ranks that passed no host array."""
+    ``(global_indices [num_pts], rows [num_pts, d])``.
+
+    Per call: one MIN all-reduce of the statistics; per pick: one all-gather of the ranks' {merit, index, row} records
+    -- every rank then finds the winner on its own device (`b200rbf_shard_apply`), so there is no broadcast and no host
+    round trip -- and, except after the last pick, one MIN all-reduce of the refreshed distance statistics.  The picks
+    are read back once, at the end."""
     import torch
     import torch.distributed as dist
 
     world = dist.get_world_size(group) if dist.is_initialized() else 1
-    rank = dist.get_rank(group) if dist.is_initialized() else 0
     m_local = int(cand_local.shape[0])
     d = int(cand_local.shape[1])
-    # contiguous row blocks: global index = offset + local index (keeps lowest-index tie breaking global)
-    counts = torch.zeros(world, dtype=torch.int64, device=backend.device)
-    counts[rank] = m_local
-    if world > 1:
-        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
-    counts = counts.cpu().tolist()
-    offsets = np.concatenate(([0], np.cumsum(counts)))
-    offset = int(offsets[rank])
+    if offset is None:
+        offset = shard_offset(m_local, backend, group)
 
     stats = backend.score(cand_local, Xdist, alias)  # {fmin, -fmax, dmin, -dmax}
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MIN, group=group)
-    picked, rows = [], []
+    results = backend.new(num_pts * (2 + d), torch.float64).view(num_pts, 2 + d)
     for i in range(num_pts):
-        pair = backend.argmin(float(weights[i]), dtol, stats, offset)
+        rec = backend.best(float(weights[i]), dtol, stats, offset)
         if world > 1:
-            allp = torch.empty(2 * world, dtype=pair.dtype, device=pair.device)
-            dist.all_gather_into_tensor(allp, pair, group=group)
+            gathered = backend.new(world * (2 + d), torch.float64)
+            dist.all_gather_into_tensor(gathered, rec, group=group)
         else:
-            allp = pair
-        host = allp.cpu().contiguous()
-        vals = host[0::2].numpy()
-        idxs = host.view(torch.int64)[1::2].numpy()
-        bv, bi = float(vals[0]), int(idxs[0])
-        for r in range(1, world):
-            if _better(float(vals[r]), int(idxs[r]), bv, bi):
-                bv, bi = float(vals[r]), int(idxs[r])
-        owner = int(np.searchsorted(offsets, bi, side="right") - 1)
-        picked.append(bi)
+            gathered = rec
         last = i + 1 == num_pts
-        # the owner poisons fvals[jj] and publishes the row; everyone folds it into dmerit
-        if rank == owner:
-            row = backend.take(bi - offset)
-        else:
-            row = backend.new(d, torch.float64)
-        if world > 1:
-            dist.broadcast(row, src=dist.get_global_rank(group, owner) if group is not None else owner, group=group)
-        rows.append(row.cpu().numpy().copy())
+        # the owner poisons fvals[jj]; everyone folds the winning row into dmerit (candidate_srbf.py:50-55)
+        new_stats = backend.apply(gathered, world, offset, not last, results[i])
         if not last:
-            new_stats = backend.update(row)
             if world > 1:
                 dist.all_reduce(new_stats, op=dist.ReduceOp.MIN, group=group)
             stats[2:] = new_stats[2:]  # fvals' min/max are computed once (candidate_srbf.py:40)
+    host = results.cpu()  # the only device -> host read of the call
     backend.finish()
-    return np.array(picked, dtype=np.int64), np.vstack(rows)
+    picked = host[:, 1].contiguous().view(torch.int64).numpy().copy()
+    return picked, host[:, 2:].numpy().copy()
 
 
-def sharded_weighted_distance_merit(num_pts, surrogate, X, fX, cand_local, weights, Xpend=None, dtol=1e-3, group=None):
+def sharded_weighted_distance_merit(num_pts, surrogate, X, fX, cand_local, weights, Xpend=None, dtol=1e-3, group=None,
+                                    offset=None):
     """weighted_distance_merit with ``cand`` split by rows over the ranks of ``group``.
 
     ``surrogate`` is this rank's GpuRBFInterpolant replica (same points on every rank).  ``cand_local`` is this
-    rank's block of rows (numpy array or float64 CUDA tensor).  Returns ``(new_points, global_indices)``.
+    rank's block of rows (numpy array or float64 CUDA tensor; it may be empty).  ``offset``: global index of its first
+    row when the caller knows it (e.g. equal blocks: rank * rows), else it is derived with one all-gather.  Returns
+    ``(new_points, global_indices)``.
     """
     X = np.asarray(X, dtype=np.float64)
     if Xpend is None:
@@ -142,5 +172,5 @@ def sharded_weighted_distance_merit(num_pts, surrogate, X, fX, cand_local, weigh
     Xdist = np.vstack((X, Xpend))
     surrogate._fit()
     alias = X.shape == surrogate.X.shape and np.array_equal(X, surrogate.X)
-    idx, rows = sharded_select(GpuShardBackend(surrogate), cand_local, Xdist, alias, weights, num_pts, dtol, group)
+    idx, rows = sharded_select(GpuShardBackend(surrogate), cand_local, Xdist, alias, weights, num_pts, dtol, group, offset)
     return rows, idx

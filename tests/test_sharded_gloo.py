@@ -2,8 +2,8 @@
 
 The product backend (GpuShardBackend) calls the C ABI phase functions on a B200; here a numpy backend with the
 same interface (built from the oracle's formulas) stands in, so offsets, the MIN all-reduce of
-{fmin,-fmax,dmin,-dmax}, the (merit, index) all-gather with lowest-index tie breaking, owner lookup and the
-winner-row broadcast are exercised end to end and compared with the unsharded oracle.
+{fmin,-fmax,dmin,-dmax}, the {merit, index, row} all-gather with lowest-index tie breaking and the device-side
+winner decision (empty shards included) are exercised end to end and compared with the unsharded oracle.
 """
 import os
 import socket
@@ -28,16 +28,26 @@ class NumpyShardBackend:
         return torch.zeros(n, dtype=dtype)
 
     def _stats(self):
+        if self.cand.shape[0] == 0:
+            return torch.full((4,), float("inf"), dtype=torch.float64)
         return torch.tensor([self.fmin, -self.fmax, self.dm.min(), -self.dm.max()], dtype=torch.float64)
 
     def score(self, cand, Xdist, alias):
         self.cand = cand
+        if cand.shape[0] == 0:
+            return self._stats()
         self.fv = self.o.predict(cand).ravel()
         self.dm = ssd.cdist(cand, Xdist).min(axis=1)
         self.fmin, self.fmax = self.fv.min(), self.fv.max()
         return self._stats()
 
-    def argmin(self, w, dtol, stats, offset):
+    def best(self, w, dtol, stats, offset):
+        d = self.cand.shape[1]
+        out = torch.zeros(2 + d, dtype=torch.float64)
+        if self.cand.shape[0] == 0:
+            out[0] = float("inf")
+            out[1:2].view(torch.int64)[0] = 0x7FFFFFFFFFFFFFFF
+            return out
         fmn, fmx, dmn, dmx = stats[0].item(), -stats[1].item(), stats[2].item(), -stats[3].item()
         with np.errstate(invalid="ignore", divide="ignore"):
             fh = np.where(np.isinf(self.fv), self.fv, np.ones_like(self.fv) if fmx == fmn else (self.fv - fmn) / (fmx - fmn))
@@ -45,17 +55,23 @@ class NumpyShardBackend:
             merit = w * fh + (1.0 - w) * (1.0 - dh)
         merit[self.dm < dtol] = np.inf
         j = int(np.argmin(merit))
-        out = torch.zeros(2, dtype=torch.float64)
         out[0] = merit[j]
-        out.view(torch.int64)[1] = j + offset
+        out[1:2].view(torch.int64)[0] = j + offset
+        out[2:] = torch.from_numpy(self.cand[j])
         return out
 
-    def take(self, local_idx):
-        self.fv[local_idx] = np.inf
-        return torch.from_numpy(self.cand[local_idx].copy())
+    def apply(self, gathered, world, offset, update, result):
+        from pysot_b200.sharded import _winner_record
 
-    def update(self, row):
-        self.dm = np.minimum(self.dm, ssd.cdist(self.cand, row.numpy()[None, :]).ravel())
+        rec = _winner_record(torch, gathered.view(world, -1))
+        result.copy_(rec)
+        j = int(rec[1:2].view(torch.int64)[0]) - offset
+        if 0 <= j < self.cand.shape[0]:
+            self.fv[j] = np.inf
+        if not update:
+            return None
+        if self.cand.shape[0] > 0:
+            self.dm = np.minimum(self.dm, ssd.cdist(self.cand, rec[2:].numpy()[None, :]).ravel())
         return self._stats()
 
     def finish(self):
@@ -121,6 +137,41 @@ def test_two_rank_selection_matches_unsharded_oracle():
     for rank, idx, rows in res:
         assert idx == tr["picked"].tolist(), (rank, idx, tr["picked"])
         assert np.array_equal(np.array(rows), ref_pts)
+
+
+def _worker3(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from pysot_b200.sharded import sharded_select
+
+        orc, o, X, fX, Xpend, cand = _case(2)
+        bounds = [0, 400, 400, cand.shape[0]]  # rank 1 holds NO candidates (it must still take part)
+        local = cand[bounds[rank]:bounds[rank + 1]]
+        idx, rows = sharded_select(NumpyShardBackend(o), local, np.vstack((X, Xpend)), True, [0.3, 0.9], 2, 1e-3)
+        q.put((rank, idx.tolist(), rows.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_three_ranks_one_empty_shard():
+    orc, o, X, fX, Xpend, cand = _case(2)
+    tr = {}
+    ref_pts = orc.weighted_distance_merit(2, o, X, fX, cand.copy(), [0.3, 0.9], Xpend, 1e-3, trace=tr)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker3, args=(r, 3, port, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, idx, rows in res:
+        assert idx == tr["picked"].tolist() and np.array_equal(np.array(rows), ref_pts), (rank, idx)
 
 
 def test_single_process_path_and_tie_rule():
