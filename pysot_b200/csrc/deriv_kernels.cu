@@ -5,7 +5,7 @@
 // s_j = phi'(r_j) c_j / r_j; phase 2 (thread per coordinate x center slice) accumulates (u_k - u_jk) s_j in
 // the reference's operation order; a second tiny kernel adds the slab partials in slab order, the tail
 // derivative (tails/linear_tail.py:46, constant_tail.py:44) and divides by the box width (rbf.py:215).
-#include "deriv_tile.cuh"
+#include "deriv_mma.cuh"
 
 namespace b200rbf {
 int ensure_tps_table(b200rbf_ctx* h);  // api.cu
@@ -101,8 +101,29 @@ __global__ void deriv_final_kernel(const double* __restrict__ partial, int nslab
 int launch_deriv(b200rbf_ctx* h, const double* x, long long m, const double* lb, const double* range, double* out,
                  double* scratch) {
   const Model& M = h->model;
+  if (m >= kDerivTileMinQueries && M.dpad <= kMaxRegDim && M.kernel != B200RBF_KERNEL_LINEAR && h->mma_dist) {
+    // enough queries to fill the GPU: distances AND the scaled accumulations as two chained DMMA GEMMs (deriv_mma.cuh)
+    DerivMmaArgs a;
+    a.x = x; a.m = m; a.d = M.d; a.lb = lb; a.range = range;
+    a.pts = M.aug ? M.centers_m.as<double>() : M.centers_x.as<double>();
+    a.cnorm = M.cnorm.as<double>(); a.coef = M.coef.as<double>(); a.tailc = M.tailc.as<double>();
+    a.ds = M.ds; a.npad = M.npad; a.tail = M.tail; a.out = out;
+    a.tps_table = nullptr;
+    if (M.kernel == B200RBF_KERNEL_TPS) {
+      B2_TRY(ensure_tps_table(h));
+      a.tps_table = h->tps_table.as<double2>();
+    }
+    const int k4 = (M.d + 3) / 4;
+    switch ((k4 - 1) / 4) {
+      case 0: return launch_deriv_mma_group0(h, a, k4, M.kernel, M.aug);
+      case 1: return launch_deriv_mma_group1(h, a, k4, M.kernel, M.aug);
+      case 2: return launch_deriv_mma_group2(h, a, k4, M.kernel, M.aug);
+      default: return launch_deriv_mma_group3(h, a, k4, M.kernel, M.aug);
+    }
+  }
   if (m >= kDerivTileMinQueries && M.dpad <= kMaxRegDim) {
-    // enough queries to fill the GPU with one thread each: the tile-streaming kernel (deriv_tile.cuh)
+    // the linear kernel (s = w / r is unbounded at coincident points) and B200RBF_OPT_MMA_DIST = 0: one thread per
+    // query, direct differences (deriv_tile.cuh)
     DerivTileArgs a;
     a.x = x; a.m = m; a.d = M.d; a.lb = lb; a.range = range;
     a.pts = M.centers_x.as<double>(); a.coef = M.coef.as<double>(); a.tailc = M.tailc.as<double>();

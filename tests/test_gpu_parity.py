@@ -579,3 +579,35 @@ def test_fit_with_large_tail_dimension(pb, orc, d):
     assert relmax(s.predict(q), o.predict(q)) < TOL
     assert s.handle.last_fit_method == ("cholesky" if d < 160 else "lu")
     assert relmax(s.predict_deriv(q[:4]), o.predict_deriv(q[:4])) < TOL
+
+
+@pytest.mark.parametrize("kernel,d,n", [("tps", 10, 3000), ("cubic", 20, 2500), ("cubic", 50, 1200), ("tps", 9, 700), ("cubic", 8, 900),
+                                        ("tps", 31, 600), ("cubic", 1, 300), ("tps", 2, 300)])
+def test_gradient_on_the_tensor_path_against_oracle(pb, orc, kernel, d, n):
+    """deriv_mma_kernel (>= 4096 queries, cubic / TPS): grad = u sum_j s_j - S C as two chained DMMA GEMMs.  Queries on
+    a clustered, optimiser-like cloud: some coincide with centers, some sit 1e-7 .. 1e-3 away (the near-pair path), the
+    rest are spread over the box; every dimension class of the fragments (d mod 8) appears in the parametrisation."""
+    rng = np.random.default_rng(1000 * d + n)
+    lb, ub = rng.uniform(-3, 0, d), rng.uniform(1, 4, d)
+    X = lb + (ub - lb) * rng.random((n, d))
+    X[n // 2:] = np.clip(X[7] + 0.03 * (ub - lb) * rng.standard_normal((n - n // 2, d)), lb, ub)  # a tight cluster
+    fX = np.sin(((X - lb) / (ub - lb)).sum(1) * 2)[:, None]
+    s = make_gpu(pb, d, lb, ub, kernel, "linear")
+    s.add_points(X, fX)
+    o = orc.OracleRBF(d, lb, ub, kernel, "linear")
+    o.add_points(X, fX)
+    m = 4096 + 37
+    q = lb + (ub - lb) * rng.random((m, d))
+    q[:64] = X[rng.integers(0, n, 64)]
+    for i, eps in enumerate((1e-7, 1e-5, 1e-3)):
+        sl = slice(64 + 64 * i, 128 + 64 * i)
+        q[sl] = np.clip(X[rng.integers(0, n, 64)] + eps * (ub - lb) * rng.standard_normal((64, d)), lb, ub)
+    got = s.predict_deriv(q)
+    pick = np.r_[0:320, m - 60:m]
+    ref = o.predict_deriv(q[pick])
+    err = relmax(got[pick], ref)
+    s.handle.set_option(2 + 4, 0)  # B200RBF_OPT_MMA_DIST = 0: the direct-difference tile kernel on the same queries
+    direct = s.predict_deriv(q)
+    print("%s d=%d n=%d: tensor path vs oracle %.2e, direct tile kernel vs oracle %.2e" % (kernel, d, n, err, relmax(direct[pick], ref)))
+    assert err < TOL and relmax(direct[pick], ref) < TOL
+    assert relmax(got, direct) < TOL
