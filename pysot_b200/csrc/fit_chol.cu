@@ -546,7 +546,7 @@ int chol_fit_weights(b200rbf_ctx* h, const double* Xu_dev, const double* f_dev, 
   size_t need = 0;
   auto take = [&](size_t cnt) { size_t off = need; need += (cnt + 15) & ~(size_t)15; return off; };
   const size_t oP = take((size_t)rcap * tp), oQn = take((size_t)n16 * tp), oW = take((size_t)rcap * tp);
-  const size_t oAc = take((size_t)n16 * 3 * tp), oBc = take((size_t)3 * tp * ld), oT21 = take((size_t)kOuter * ld);
+  const size_t oAc = take((size_t)n16 * 3 * tp), oBc = take((size_t)3 * tp * ld), oT21 = take((size_t)2 * kOuter * ld);
   const size_t oG = take((size_t)tp * tp), oR1 = take((size_t)tp * tp);
   const size_t oR2 = take((size_t)tp * tp), oR = take((size_t)tp * tp), oS = take((size_t)tp * tp);
   const size_t oGp = take((size_t)nparts * tp * tp), oV0 = take(rcap), oV1 = take(rcap), oV2 = take(rcap), oq = take(tp);
@@ -626,28 +626,59 @@ int chol_fit_weights(b200rbf_ctx* h, const double* Xu_dev, const double* f_dev, 
   // The inverses of the diagonal blocks are kept for step 6.
   const size_t sm_pi = ((size_t)kNB * (kNB + 1) + 3 * 32 * 33) * sizeof(double);
   B2_CUDA(cudaFuncSetAttribute(potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pi));
-  for (int J0 = 0; J0 < n16; J0 += kOuter) {
-    const int R0 = (J0 + kOuter < n16) ? J0 + kOuter : n16;  // first column right of the outer panel
-    for (int j0 = J0; j0 < R0; j0 += kNB) {
-      const int nb = (n16 - j0 < kNB) ? (n16 - j0) : kNB;
-      const int r0 = j0 + nb, rows = n16 - r0;
-      potrf_inv_kernel<<<1, kPiThreads, sm_pi, h->stream>>>(A, ld, j0, nb, w.Linv + (size_t)(j0 / kNB) * kNB * kNB,
-                                                            w.LinvT, info_dev);
-      LAUNCHED(h);
-      if (rows <= 0) break;
-      double* A21 = A + (size_t)r0 * ld + j0;
-      double* T21 = w.T21 + (size_t)(j0 - J0) * ld + r0;  // T21[k][r - r0] = L[r][j0 + k]
-      B2_CUDA(cudaMemsetAsync(w.Tn, 0, (size_t)rows * kNB * sizeof(double), h->stream));
-      B2_TRY(gemm_sub_ex(h, w.Tn, kNB, A21, ld, w.LinvT, kNB, rows, nb, nb, 0));
-      dim3 blk(32, 8), grd((nb + 31) / 32, (rows + 31) / 32);
-      finish_panel_kernel<<<grd, blk, 0, h->stream>>>(w.Tn, rows, nb, A21, ld, T21, ld);
-      LAUNCHED(h);
-      if (r0 < R0)  // the rest of the outer panel: rows >= r0, columns [r0, R0)
-        B2_TRY(gemm_sub_ex(h, A + (size_t)r0 * ld + r0, ld, A21, ld, T21, ld, rows, R0 - r0, nb, 1));
+  // Look-ahead across outer panels.  The trailing update of outer panel J is split into C1 (the 512 columns of the NEXT
+  // outer panel) and C2 (everything right of those).  As soon as C1 is done the next panel's chain -- 4 x (one-CTA
+  // factorisation + inverse, panel GEMM, store, in-panel update: ~1 ms of launches that cannot fill the GPU) -- runs on
+  // the high-priority stream WHILE C2, one big K = 512 GEMM, keeps the SMs busy on the main stream: the panel's CTAs
+  // take the slots that retiring GEMM CTAs free.  L21^T is double-buffered (C2 of panel J reads buffer J & 1 while panel
+  // J + 1 writes the other).  The first version ran everything in one stream: 157 x 75 us of potrf_inv_kernel alone
+  // (10 % of the fit at N = 20 000) with 147 SMs idle.
+  {
+    cudaStream_t s_main = h->stream, s_la = h->la_stream;
+    struct StreamGuard {  // every error return puts the handle's stream back
+      b200rbf_ctx* h;
+      cudaStream_t s;
+      ~StreamGuard() { h->stream = s; }
+    } stream_guard{h, s_main};
+    B2_CUDA(cudaEventRecord(h->ev_la1, s_main));  // the assembled matrix
+    B2_CUDA(cudaStreamWaitEvent(s_la, h->ev_la1, 0));
+    int pj = 0;
+    for (int J0 = 0; J0 < n16; J0 += kOuter, ++pj) {
+      const int R0 = (J0 + kOuter < n16) ? J0 + kOuter : n16;  // first column right of the outer panel
+      double* T21b = w.T21 + (size_t)(pj & 1) * kOuter * ld;
+      h->stream = s_la;
+      for (int j0 = J0; j0 < R0; j0 += kNB) {
+        const int nb = (n16 - j0 < kNB) ? (n16 - j0) : kNB;
+        const int r0 = j0 + nb, rows = n16 - r0;
+        potrf_inv_kernel<<<1, kPiThreads, sm_pi, h->stream>>>(A, ld, j0, nb, w.Linv + (size_t)(j0 / kNB) * kNB * kNB,
+                                                              w.LinvT, info_dev);
+        LAUNCHED(h);
+        if (rows <= 0) break;
+        double* A21 = A + (size_t)r0 * ld + j0;
+        double* T21 = T21b + (size_t)(j0 - J0) * ld + r0;  // T21[k][r - r0] = L[r][j0 + k]
+        B2_CUDA(cudaMemsetAsync(w.Tn, 0, (size_t)rows * kNB * sizeof(double), h->stream));
+        B2_TRY(gemm_sub_ex(h, w.Tn, kNB, A21, ld, w.LinvT, kNB, rows, nb, nb, 0));
+        dim3 blk(32, 8), grd((nb + 31) / 32, (rows + 31) / 32);
+        finish_panel_kernel<<<grd, blk, 0, h->stream>>>(w.Tn, rows, nb, A21, ld, T21, ld);
+        LAUNCHED(h);
+        if (r0 < R0)  // the rest of the outer panel: rows >= r0, columns [r0, R0)
+          B2_TRY(gemm_sub_ex(h, A + (size_t)r0 * ld + r0, ld, A21, ld, T21, ld, rows, R0 - r0, nb, 1));
+      }
+      B2_CUDA(cudaEventRecord(h->ev_la2, s_la));  // panel pj factored, its L21^T complete
+      h->stream = s_main;
+      B2_CUDA(cudaStreamWaitEvent(s_main, h->ev_la2, 0));
+      if (R0 < n16) {
+        const int R1 = (R0 + kOuter < n16) ? R0 + kOuter : n16;
+        // C1: the next outer panel's columns [R0, R1), rows >= R0
+        B2_TRY(gemm_sub_ex(h, A + (size_t)R0 * ld + R0, ld, A + (size_t)R0 * ld + J0, ld, T21b + R0, ld, n16 - R0, R1 - R0,
+                           R0 - J0, 1));
+        B2_CUDA(cudaEventRecord(h->ev_la1, s_main));
+        B2_CUDA(cudaStreamWaitEvent(s_la, h->ev_la1, 0));  // the next panel may start; C2 of this one overlaps it
+        if (R1 < n16)  // C2: everything right of the next panel, K = R0 - J0
+          B2_TRY(gemm_sub_ex(h, A + (size_t)R1 * ld + R1, ld, A + (size_t)R1 * ld + J0, ld, T21b + R1, ld, n16 - R1, n16 - R1,
+                             R0 - J0, 1));
+      }
     }
-    if (R0 < n16)  // everything right of the outer panel, K = R0 - J0
-      B2_TRY(gemm_sub_ex(h, A + (size_t)R0 * ld + R0, ld, A + (size_t)R0 * ld + J0, ld, w.T21 + R0, ld, n16 - R0, n16 - R0,
-                         R0 - J0, 1));
   }
   // 6. c = Pi L^-T L^-1 Pi f : two single-launch pipelined triangular solves (fit_extend.cu) with the stored inverses
   // of the diagonal blocks.  bvec = Pi f and u = L^-1 Pi f are kept: an extension appends to them.
