@@ -61,8 +61,9 @@ enum {
    *    d = 50, relative error of r^2 <= ~1e-12; square roots / logarithms built from the hardware seeds, <= 1 ulp).
    *    0: direct differences everywhere.  Ignored when EXACT_DIST is set.                                        */
   B200RBF_OPT_MMA_DIST = 6,
-  /* solver of b200rbf_fit: 0 (default) auto = null-space Cholesky for cubic / TPS + linear tail with n >= 128, pivoted
-   *    LU otherwise and whenever the Cholesky reports a non-positive pivot; 1 = always LU; 2 = Cholesky or error       */
+  /* solver of b200rbf_fit: 0 (default) auto = null-space Cholesky for cubic / TPS + linear tail with n >= 2 ntail + 32
+   *    and dim <= 159, pivoted LU otherwise and whenever the Cholesky reports a non-positive pivot; 1 = always LU;
+   *    2 = Cholesky or error                                                                                         */
   B200RBF_OPT_FIT_METHOD = 7,
   /* 1 (default): a Cholesky fit of n <= 8192 points pre-allocates room for 2 n (at least 1024) so that b200rbf_extend
    *    can append points in place; 0: never keep an extendable factorisation                                      */

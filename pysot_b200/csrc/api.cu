@@ -545,7 +545,7 @@ int b200rbf_fit(b200rbf_handle h, const double* Xu, const double* rhs, int n, in
   bool done = false, installed = false;
   ExtState& E = h->fit.ext;
   E.valid = false;
-  if (chol_ok && (h->fit_method == 2 || (h->fit_method == 0 && n >= 128))) {
+  if (chol_ok && h->fit_method != 1) {  // faster than the LU from the smallest admissible size on (tools/fit_small.py)
     B2_TRY(ensure_fit_sync(h));
     TrsvSync* sy = h->fit.sync.as<TrsvSync>();
     int* info_dev = &sy->info;

@@ -5,7 +5,7 @@ import numpy as np
 import pysot_b200 as pb
 from pysot_b200 import _lib
 for d in (10, 30):
-    for n in (80, 150, 300, 500, 700, 1000, 1500):
+    for n in (56, 64, 80, 100, 127, 150, 300, 500, 1000):
         if n < 2 * (d + 1) + 32: continue
         rng = np.random.default_rng(0)
         X = rng.random((n, d)); fX = np.sin(3 * X.sum(1))[:, None]
@@ -13,7 +13,7 @@ for d in (10, 30):
         for method in (1, 2):
             s = pb.GpuRBFInterpolant(dim=d, lb=np.zeros(d), ub=np.ones(d))
             s.handle.set_option(_lib.OPT_FIT_METHOD, method)
-            s.add_points(X, fX); s._fit()
+            s.add_points(X, fX); s._fit(); s._incremental = False
             ts = []
             for r in range(10):
                 s.updated = False; t0 = time.perf_counter(); s._fit(); ts.append(time.perf_counter() - t0)
