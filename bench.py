@@ -475,20 +475,32 @@ def run_native(args, rank, world, local_rank):
     tpath = os.path.join(ROOT, "profiles", "score_kernel_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            traffic = tj.get("dram_bytes_per_launch_" + h.last_score_kernel, tj.get("dram_bytes_per_launch"))
         except Exception:
             traffic = None
+    which = h.last_score_kernel
+    if which == "int8":
+        kname = ("score_i8_kernel<NK=2, cubic> (norm-expansion distances; dot products on the INT8 tensor cores: tcgen05.mma.kind::i8, "
+                 "six base-256 digit planes of the 46-bit fixed-point coordinates, exact int32 accumulation in TMEM; near pairs recomputed)")
+        knote = ("achieved counts SURVEY 8(d)'s ALGORITHMIC 3d+6 flops per pair (direct differences). The kernel executes 52 int8 MMAs "
+                 "(M128 N64 K32) per 128 x 64 pairs on the tensor cores + ~12 FP64 and ~20 integer operations per pair; on sm_100a the "
+                 "tcgen05 MMAs and FP64 instructions time-share (measured additive, tools/umma_overlap.cu), so the launch time is "
+                 "MMA + drain + FP64 epilogue; a fraction above 1 is arithmetic moved off the FP64 datapath, not a faster pipe")
+    else:
+        kname = "score_mma_kernel<K4=13, cubic> (norm-expansion distances, DMMA dot products, near pairs recomputed)"
+        knote = ("achieved counts SURVEY 8(d)'s ALGORITHMIC 3d+6 flops per pair (direct differences); the kernel executes "
+                 "2*52 (DMMA) + 7 on the shared FP64 FMA/DMMA datapath, so a fraction above 1 is arithmetic savings, not a faster pipe "
+                 "(ncu: that datapath is 87.5 % busy)")
     roofline = {
-        "kernel": "score_mma_kernel<K4=13, cubic> (norm-expansion distances, DMMA dot products, near pairs recomputed)",
+        "kernel": kname, "kernel_id": which,
         "bound": "tensor", "bound_detail": "FP64: DMMA (fp64 tensor op) and DFMA share one datapath on sm_100a (measured: "
                                            "36.5 vs 36.6 TFLOP/s, 36.0 interleaved); the bf16 tensor peak does not apply; HBM traffic is < 0.1 % of its peak",
         "achieved": k_tflops,
         "peak": peaks["dfma_tflops"], "unit": "TFLOP/s", "frac": k_tflops / peaks["dfma_tflops"],
         "peak_source": "b200rbf_fp64_peaks: dependency-free DFMA loop on this device, 300 ms (MEASURED_PEAKS.json has no fp64 entry)",
         "flops_per_pair": FLOPS_PER_PAIR,
-        "note": "achieved counts SURVEY 8(d)'s ALGORITHMIC 3d+6 flops per pair (direct differences); the kernel executes "
-                "2*52 (DMMA) + 7 on the shared FP64 FMA/DMMA datapath, so a fraction above 1 is arithmetic savings, not a faster pipe "
-                "(ncu: that datapath is 87.5 % busy)",
+        "note": knote,
         "launch_ms": k_ms, "share_of_step": k_ms * args.steps / dev_ms,
         "dmma_peak_tflops": peaks["dmma_tflops"], "traffic": traffic,
         "hbm": {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (k_ms * 1e-3) / 1e9, "peak_gbs": mp["hbm_gbs"],

@@ -67,7 +67,13 @@ enum {
   B200RBF_OPT_FIT_METHOD = 7,
   /* 1 (default): a Cholesky fit of n <= 8192 points pre-allocates room for 2 n (at least 1024) so that b200rbf_extend
    *    can append points in place; 0: never keep an extendable factorisation                                      */
-  B200RBF_OPT_INCREMENTAL = 8
+  B200RBF_OPT_INCREMENTAL = 8,
+  /* -1 (default) auto = from dim 40 on, 1 = always, 0 = never: the dot products of the norm expansion run on the INT8
+   *    tensor cores (tcgen05.mma.kind::i8, accumulators in TMEM): unit-box coordinates are 46-bit fixed-point numbers split
+   *    into six base-256 digit planes, the digit products of equal weight accumulate exactly in int32 (score_i8.cu; error
+   *    in r^2 below that of the FP64 norm expansion).  A call whose coordinates leave [0, 1] is re-run on the FP64 tensor
+   *    path.  Ignored with EXACT_DIST, with MMA_DIST = 0 and for dim > 128.                                         */
+  B200RBF_OPT_I8_DIST = 9
 };
 
 const char* b200rbf_last_error(void);
@@ -190,6 +196,9 @@ long long b200rbf_launch_count(b200rbf_handle h);
 double b200rbf_last_score_ms(b200rbf_handle h);
 /* Solver the last b200rbf_fit / b200rbf_extend used: 1 = pivoted LU, 2 = null-space Cholesky, 3 = row-append extension. */
 int b200rbf_last_fit_method(b200rbf_handle h);
+/* Kernel that computed the surrogate values of the last b200rbf_predict / b200rbf_score: 1 = direct differences
+ * (score_kernel), 2 = FP64 tensor path (score_mma_kernel), 3 = INT8 tensor cores (score_i8_kernel), 4 = direct, d > 64. */
+int b200rbf_last_score_kernel(b200rbf_handle h);
 
 /* ---- test hooks: exercise the factorisation pieces in isolation (tests/ only, not the drop-in surface) ----
  * dbg_lu  : A_host is N x (N + nrhs) row-major; on return the leading N x N block holds L\U (unit lower L),

@@ -14,6 +14,7 @@ KERNEL_CUBIC, KERNEL_TPS, KERNEL_LINEAR = 0, 1, 2
 TAIL_LINEAR, TAIL_CONSTANT = 0, 1
 OPT_EXACT_DIST, OPT_CHUNK_ROWS, OPT_LU_PANEL, OPT_LU_LOOKAHEAD, OPT_GEMM_STAGES, OPT_MMA_DIST, OPT_FIT_METHOD = 1, 2, 3, 4, 5, 6, 7
 OPT_INCREMENTAL = 8
+OPT_I8_DIST = 9
 E_INVAL, E_CUDA, E_STATE, E_SINGULAR, E_NOMEM, E_REFIT = -1, -2, -3, -4, -5, -6
 
 _dp = C.POINTER(C.c_double)
@@ -46,6 +47,7 @@ PROTOTYPES = {
     "b200rbf_launch_count": (C.c_longlong, [_vp]),
     "b200rbf_last_score_ms": (C.c_double, [_vp]),
     "b200rbf_last_fit_method": (C.c_int, [_vp]),
+    "b200rbf_last_score_kernel": (C.c_int, [_vp]),
     "b200rbf_dbg_lu": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp]),
     "b200rbf_dbg_gemm": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _dp]),
 }
@@ -145,6 +147,10 @@ class Handle:
     @property
     def last_fit_method(self):
         return {1: "lu", 2: "cholesky", 3: "extension"}.get(int(load().b200rbf_last_fit_method(self._h)), "none")
+
+    @property
+    def last_score_kernel(self):
+        return {1: "direct", 2: "dmma", 3: "int8", 4: "direct-generic"}.get(int(load().b200rbf_last_score_kernel(self._h)), "none")
 
     # ---- model
     def fit(self, Xu, rhs, kernel, tail, eta):

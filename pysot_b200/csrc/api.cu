@@ -155,6 +155,8 @@ int install_model(b200rbf_ctx* h, const double* Xu_dev, const double* c_dev, int
   h->launches++;
   B2_CUDA(cudaGetLastError());
   M.loaded = true;
+  M.i8_ready = false;
+  M.i8_bad = false;
   h->score.valid = false;
   return 0;
 }
@@ -195,8 +197,15 @@ int block_rows(int dpad) {
   return kMmaRowsPerCta < kScoreThreads ? kMmaRowsPerCta : kScoreThreads;
 }
 bool use_mma(const b200rbf_ctx* h, bool with_phi);
+bool use_i8(const b200rbf_ctx* h, bool with_phi) {
+  // auto (-1): from d = 40 on the int8 kernel beats the DMMA kernel (1.03x at 40, 1.28x at 50, 1.42x at 64) and, above
+  // d = 64, the direct kernel that was the only one there (8x at 96, 15x at 128); tools/i8_sweep.py
+  const bool want = h->i8_dist == 1 || (h->i8_dist < 0 && h->model.d >= 40);
+  return with_phi && want && h->mma_dist && !h->i8_veto && !h->model.i8_bad && !h->exact_dist && h->model.d <= 128;
+}
 // candidates per CTA of the kernel that computes surrogate values / of the distance-only kernel
 int main_rows(const b200rbf_ctx* h) {
+  if (use_i8(h, true)) return i8_rows_per_cta();
   if (h->model.dpad > kMaxRegDim) return score_generic_threads();
   return use_mma(h, true) ? kMmaRowsPerCta : kScoreThreads;
 }
@@ -231,7 +240,10 @@ int launch_score_mma(b200rbf_ctx* h, const ScoreArgs& a) {
 }
 
 int launch_score_any(b200rbf_ctx* h, const ScoreArgs& a, int dpad, int kernel, bool exact, bool with_phi) {
-  if (use_mma(h, with_phi)) return launch_score_mma(h, a);
+  const int which = use_i8(h, with_phi) ? 3 : use_mma(h, with_phi) ? 2 : dpad > kMaxRegDim ? 4 : 1;
+  if (with_phi && a.occ_out == nullptr) h->last_score_kernel = which;
+  if (which == 3) return launch_score_i8(h, a);
+  if (which == 2) return launch_score_mma(h, a);
   if (dpad > kMaxRegDim) return launch_score_generic(h, a, dpad, kernel, exact, with_phi);
   switch ((dpad - 2) / 8) {
     case 0: return launch_score_group0(h, a, dpad, kernel, exact, with_phi);
@@ -361,6 +373,26 @@ int score_pipeline(b200rbf_ctx* h, const ScorePlan& plan, const double* cand, lo
   return 0;
 }
 
+// ---- int8 score kernel: coordinates outside the unit box (or a fault in the tensor-core pipeline) are reported through
+// two device flags; they are fetched with the call's final synchronisation and the call is repeated on the DMMA kernel
+int* i8_flags_host(b200rbf_ctx* h) { return reinterpret_cast<int*>(h->pin_small.p) + 2 * 4000; }
+int i8_queue_flags(b200rbf_ctx* h, bool used) {
+  if (!used || !h->model.i8_ready) return 0;
+  B2_CUDA(cudaMemcpyAsync(i8_flags_host(h), h->model.i8_flag.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  return 0;
+}
+int i8_after_sync(b200rbf_ctx* h, bool used, bool* retry) {
+  *retry = false;
+  if (!used || !h->model.i8_ready) return 0;
+  const int* f = i8_flags_host(h);
+  if (f[0] == 0 && f[1] == 0) return 0;
+  B2_CHECK(f[1] != 2, B200RBF_ECUDA, "int8 score kernel: the tensor-core pipeline did not complete");
+  if (f[0] != 0) h->model.i8_bad = true;  // a CENTER outside the unit box: this model stays on the DMMA kernel
+  B2_CUDA(cudaMemsetAsync(h->model.i8_flag.as<int>() + 1, 0, sizeof(int), h->stream));
+  *retry = true;
+  return 0;
+}
+
 int count_parts(long long m, long long chunk, bool chunked, int br) {
   // upper bound on the per-CTA partial slots: one launch per chunk, each rounds its row count up to whole CTAs
   // (the pipeline may round `chunk` up to whole waves, which only lowers the number of launches)
@@ -434,6 +466,7 @@ int b200rbf_destroy(b200rbf_handle h) {
   Model& M = h->model;
   M.centers.release(); M.coef.release(); M.tailc.release();
   M.centers_x.release(); M.centers_m.release(); M.cnorm.release();
+  M.centers_q.release(); M.cnorm_q.release(); M.coef_q.release(); M.i8_flag.release();
   ScoreState& S = h->score;
   S.cand_own.release(); S.fvals.release(); S.dmerit.release(); S.parts.release(); S.pair_parts.release();
   S.stats.release(); S.winner.release(); S.results.release(); S.dist.release(); S.box.release();
@@ -468,6 +501,10 @@ int b200rbf_set_option(b200rbf_handle h, int option, long long value) {
   switch (option) {
     case B200RBF_OPT_EXACT_DIST: h->exact_dist = value != 0; return 0;
     case B200RBF_OPT_MMA_DIST: h->mma_dist = value != 0; return 0;
+    case B200RBF_OPT_I8_DIST:
+      B2_CHECK(value >= -1 && value <= 1, B200RBF_EINVAL, "int8 mode must be -1 (auto), 0 (off) or 1 (on)");
+      h->i8_dist = (int)value;
+      return 0;
     case B200RBF_OPT_FIT_METHOD:
       B2_CHECK(value >= 0 && value <= 2, B200RBF_EINVAL, "fit method must be 0 (auto), 1 (LU) or 2 (Cholesky)");
       h->fit_method = (int)value;
@@ -498,6 +535,7 @@ int b200rbf_set_option(b200rbf_handle h, int option, long long value) {
 long long b200rbf_launch_count(b200rbf_handle h) { return h ? h->launches : 0; }
 double b200rbf_last_score_ms(b200rbf_handle h) { return h ? h->last_score_ms : -1.0; }
 int b200rbf_last_fit_method(b200rbf_handle h) { return h ? h->last_fit_method : 0; }
+int b200rbf_last_score_kernel(b200rbf_handle h) { return h ? h->last_score_kernel : 0; }
 
 int b200rbf_load(b200rbf_handle h, const double* Xu, const double* c, int n, int d, int kernel, int tail) {
   B2_CHECK(h && Xu && c, B200RBF_EINVAL, "NULL argument");
@@ -669,7 +707,9 @@ int b200rbf_extend(b200rbf_handle h, const double* Xu, const double* rhs, int n,
   return 0;
 }
 
-int b200rbf_predict(b200rbf_handle h, const double* x, long long m, const double* lb, const double* ub, double* out) {
+static int predict_impl(b200rbf_handle h, const double* x, long long m, const double* lb, const double* ub, double* out,
+                        bool* retry) {
+  *retry = false;
   B2_CHECK(h && x && lb && ub && out, B200RBF_EINVAL, "NULL argument");
   B2_CHECK(h->model.loaded, B200RBF_ESTATE, "no model resident: call b200rbf_fit or b200rbf_load first");
   B2_CHECK(m >= 0, B200RBF_EINVAL, "negative row count");
@@ -696,8 +736,22 @@ int b200rbf_predict(b200rbf_handle h, const double* x, long long m, const double
   B2_TRY(score_pipeline(h, plan, x, m, xdev, h->tmp_box.as<double>(), fv, nullptr, parts, nparts, &used, &used_f,
                         &used_d));
   if (host_out) B2_TRY(copy_out(h, out, fv, (size_t)m * sizeof(double)));
+  const bool i8 = use_i8(h, true);
+  B2_TRY(i8_queue_flags(h, i8));
   B2_CUDA(cudaStreamSynchronize(h->stream));
+  B2_TRY(i8_after_sync(h, i8, retry));
   return 0;
+}
+
+int b200rbf_predict(b200rbf_handle h, const double* x, long long m, const double* lb, const double* ub, double* out) {
+  bool retry = false;
+  int rc = predict_impl(h, x, m, lb, ub, out, &retry);
+  if (rc == 0 && retry) {  // coordinates outside the unit box: the FP64 tensor path serves this call
+    h->i8_veto = true;
+    rc = predict_impl(h, x, m, lb, ub, out, &retry);
+    h->i8_veto = false;
+  }
+  return rc;
 }
 
 int b200rbf_predict_deriv(b200rbf_handle h, const double* x, long long m, const double* lb, const double* ub,
@@ -728,9 +782,10 @@ int b200rbf_predict_deriv(b200rbf_handle h, const double* x, long long m, const 
   return 0;
 }
 
-int b200rbf_score(b200rbf_handle h, const double* cand, long long m, const double* lb, const double* ub,
-                  const double* Xdist, int ndist, int alias_centers, double* fvals_out, double* dmerit_out,
-                  double* stats_out) {
+static int score_impl(b200rbf_handle h, const double* cand, long long m, const double* lb, const double* ub,
+                      const double* Xdist, int ndist, int alias_centers, double* fvals_out, double* dmerit_out,
+                      double* stats_out, bool* retry) {
+  *retry = false;
   B2_CHECK(h && cand && lb && ub && Xdist, B200RBF_EINVAL, "NULL argument");
   B2_CHECK(h->model.loaded, B200RBF_ESTATE, "no model resident: call b200rbf_fit or b200rbf_load first");
   B2_CHECK(m >= 1, B200RBF_EINVAL, "need at least one candidate");
@@ -791,7 +846,11 @@ int b200rbf_score(b200rbf_handle h, const double* cand, long long m, const doubl
   if (fvals_out) B2_TRY(copy_out(h, fvals_out, S.fvals.p, (size_t)m * sizeof(double)));
   if (dmerit_out) B2_TRY(copy_out(h, dmerit_out, S.dmerit.p, (size_t)m * sizeof(double)));
   if (stats_out) B2_TRY(copy_out(h, stats_out, S.stats.p, 4 * sizeof(double)));
+  const bool i8 = use_i8(h, true);
+  B2_TRY(i8_queue_flags(h, i8));
   B2_CUDA(cudaStreamSynchronize(h->stream));
+  B2_TRY(i8_after_sync(h, i8, retry));
+  if (*retry) return 0;
   {
     float ms = -1.f;
     if (cudaEventElapsedTime(&ms, h->ev_s0, h->ev_s1) != cudaSuccess) cudaGetLastError();
@@ -799,6 +858,19 @@ int b200rbf_score(b200rbf_handle h, const double* cand, long long m, const doubl
   }
   S.valid = true;
   return 0;
+}
+
+int b200rbf_score(b200rbf_handle h, const double* cand, long long m, const double* lb, const double* ub,
+                  const double* Xdist, int ndist, int alias_centers, double* fvals_out, double* dmerit_out,
+                  double* stats_out) {
+  bool retry = false;
+  int rc = score_impl(h, cand, m, lb, ub, Xdist, ndist, alias_centers, fvals_out, dmerit_out, stats_out, &retry);
+  if (rc == 0 && retry) {  // coordinates outside the unit box: the FP64 tensor path serves this call
+    h->i8_veto = true;
+    rc = score_impl(h, cand, m, lb, ub, Xdist, ndist, alias_centers, fvals_out, dmerit_out, stats_out, &retry);
+    h->i8_veto = false;
+  }
+  return rc;
 }
 
 int b200rbf_select(b200rbf_handle h, const double* weights, int p, double dtol, long long* idx_out,

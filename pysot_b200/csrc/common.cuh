@@ -151,6 +151,10 @@ struct Model {
   DevBuf centers_m;         // the same with (1, |c|^2) in slots d, d + 1 when `aug`
   bool aug = false;
   int ds = 0;
+  // operands of the int8 tensor-core score kernel (score_i8.cu), built lazily on first use
+  DevBuf centers_q, cnorm_q, coef_q, i8_flag;  // digit planes, norms of the quantised centers, weights padded to tiles,
+  bool i8_ready = false, i8_bad = false;       // {centers out of [0,1], candidates out of [0,1] / fault}
+  int i8_nk = 0, i8_ntiles = 0;
 };
 
 struct ScoreState {
@@ -227,6 +231,7 @@ struct b200rbf_ctx {
   cudaEvent_t ev_la1 = nullptr, ev_la2 = nullptr;
   int fit_method = 0;  // 0 auto (null-space Cholesky where it applies, else pivoted LU), 1 LU, 2 Cholesky or fail
   int last_fit_method = 0;  // what the last b200rbf_fit actually used (1 LU, 2 Cholesky)
+  int last_score_kernel = 0;  // value kernel of the last predict / score: 1 direct, 2 DMMA, 3 int8 tensor cores, 4 generic (d > 64)
   bool lu_lookahead = false;  // implemented and correct, but measured to give no overlap (see include/b200rbf.h)
   int gemm_stages = 4;          // DMMA GEMM variant: 2 / 3 = cp.async stages at BK 16, 4 = 2 stages at BK 32 (default)
   bool gemm_stages_auto = true; // drop to 2 while a look-ahead panel shares the SMs
@@ -236,6 +241,8 @@ struct b200rbf_ctx {
   long long launches = 0;
   bool exact_dist = false;
   bool mma_dist = true;  // norm-expansion distances on the FP64 tensor path (score_mma.cuh) unless exact_dist
+  int i8_dist = -1;      // dot products of the norm expansion on the INT8 tensor cores (score_i8.cu): -1 auto (d >= 40), 0 off, 1 on
+  bool i8_veto = false;  // this call fell back (coordinates outside the unit box): the DMMA kernel serves it
   long long chunk_rows = 131072;  // target rows per H2D chunk; rounded to whole waves of the score kernel
   int lu_panel = 128;
   bool incremental = true;  // keep the Cholesky factorisation extendable by b200rbf_extend (pre-allocates 2x rows, n <= 8192)
@@ -272,6 +279,8 @@ struct ScoreArgs {
 };
 
 // score kernel for kMaxRegDim < dpad <= kGenMaxDim (score_generic.cu) and its candidates-per-CTA
+int launch_score_i8(b200rbf_ctx* h, const ScoreArgs& a);  // score_i8.cu
+int i8_rows_per_cta();
 int launch_score_generic(b200rbf_ctx* h, const ScoreArgs& a, int dpad, int kernel, bool exact, bool with_phi);
 int score_generic_threads();
 // parts: 4 rows {fmin, fmax, dmin, dmax} x `stride` slots, `count` of them valid; which: bit0 f rows, bit1 d rows

@@ -85,13 +85,15 @@ def test_config4_bench_shape_default_kernel_real_fit():
     assert relmax(s.predict(cand[:512]), g["fvals"][:512].reshape(-1, 1)) < 1e-10
 
 
-@pytest.mark.parametrize("variant", ["mma", "direct", "exact"])
+@pytest.mark.parametrize("variant", ["mma", "direct", "exact", "int8"])
 def test_config4_bench_shape_reference_coefficients(variant):
     """Scoring isolated from fitting: the reference's own coefficient vector is loaded into the handle."""
     g, X, fX, cand = _config4()
     s = pb.GpuRBFInterpolant(dim=50, lb=np.zeros(50), ub=np.ones(50), exact_dist=(variant == "exact"))
     if variant == "direct":
         s.handle.set_option(_lib.OPT_MMA_DIST, 0)
+    if variant == "int8":  # dot products on the INT8 tensor cores (score_i8.cu)
+        s.handle.set_option(_lib.OPT_I8_DIST, 1)
     s.add_points(X, fX)
     s.set_coefficients(g["c"])
     idx, merit, fv, dm, st = pb.merit_select_indices(4, s, X, cand, list(g["weights"]), g["Xpend"], 1e-3, want_scores=True)
