@@ -250,3 +250,48 @@ def test_nd_sorting_matches_definition_and_reference():
         if ref is not None:
             assert np.array_equal(got, ref(F.copy(), nmax)), it
     assert nd_sorting(np.zeros((2, 0)), 10).shape == (0,)
+
+
+def test_fit_decides_between_extension_and_refit():
+    """rbf.py:97-161 on the host side: extend when the points the device factorisation was built from are an unchanged
+    prefix, refit otherwise or when the library declines (Handle.extend -> None)."""
+    calls = []
+
+    class StubHandle:
+        last_fit_method = "stub"
+        decline = False
+
+        def fit(self, Xu, rhs, kid, tid, eta):
+            calls.append(("fit", Xu.shape[0]))
+            return np.zeros(Xu.shape[0] + Xu.shape[1] + 1), 0.0
+
+        def extend(self, Xu, rhs, tid, rhs_changed):
+            calls.append(("extend", Xu.shape[0], bool(rhs_changed)))
+            return None if self.decline else (np.zeros(Xu.shape[0] + Xu.shape[1] + 1), 0.0)
+
+    rng = np.random.default_rng(0)
+    s = pb.GpuRBFInterpolant(dim=3, lb=np.zeros(3), ub=np.ones(3), output_transformation=pb.median_capping)
+    s._handle = StubHandle()
+    X, f = rng.random((40, 3)), rng.random((40, 1))
+    s.add_points(X[:20], f[:20])
+    s._fit()
+    s.add_points(X[20:25], f[20:25])
+    s._fit()                                  # prefix unchanged -> extend; the median moved -> old values changed
+    s._fit()                                  # already up to date: nothing
+    s.add_points(X[25], f[25])
+    s._handle.decline = True
+    s._fit()                                  # the library declines -> full refit
+    s._handle.decline = False
+    s.reset()
+    s.add_points(X[:30], f[:30])
+    s._fit()                                  # reset: nothing to extend
+    s.add_points(X[30], f[30])
+    s._X[3, 0] += 1e-3                        # a resident point moved: refit
+    s._fit()
+    t = pickle.loads(pickle.dumps(s))
+    assert t._fit_Xu is None and t._handle is None
+    assert calls == [("fit", 20), ("extend", 25, True), ("extend", 26, True), ("fit", 26), ("fit", 30), ("fit", 31)], calls
+    plain = pb.GpuRBFInterpolant(dim=3, lb=np.zeros(3), ub=np.ones(3), incremental=False)
+    plain._handle = StubHandle()
+    plain.add_points(X[:20], f[:20]); plain._fit(); plain.add_points(X[20], f[20]); plain._fit()
+    assert calls[-2:] == [("fit", 20), ("fit", 21)]
