@@ -69,16 +69,18 @@ def test_auto_rule_and_fallback_outside_the_unit_box(orc):
     rng, lb, ub, X, fX, s, o = build(orc, "cubic", 44, 500, 3)
     m = 4000
     cand = lb + (ub - lb) * rng.random((m, 44))
+    s.predict(cand[:10])  # the fit and the lazy slicing of the centers happen here
     l0 = s.handle.launches
     p_in = s.predict(cand)  # d = 44 >= 40: the int8 kernel by default
     n_in = s.handle.launches - l0
+    assert s.handle.last_score_kernel == "int8"
     assert relmax(p_in, o.predict(cand)) < TOL
     far = cand.copy()
     far[17] = ub + 0.3 * (ub - lb)   # outside the box: u > 1 -> flagged, the call is repeated on the DMMA kernel
     far[99] = lb - 2.0 * (ub - lb)
     l0 = s.handle.launches
     p_out = s.predict(far)
-    assert s.handle.launches - l0 > n_in  # it ran twice
+    assert s.handle.launches - l0 > n_in and s.handle.last_score_kernel == "dmma"  # it ran twice
     assert relmax(p_out, o.predict(far)) < TOL
     # and through the acquisition entry point
     w = [0.4, 0.9]
@@ -89,11 +91,12 @@ def test_auto_rule_and_fallback_outside_the_unit_box(orc):
     # the next in-range call is served by the int8 kernel again
     l0 = s.handle.launches
     assert relmax(s.predict(cand), o.predict(cand)) < TOL
-    assert s.handle.launches - l0 == n_in
+    assert s.handle.launches - l0 == n_in and s.handle.last_score_kernel == "int8"
     # centers outside the box (points added beyond the bounds): the model stays on the DMMA kernel
     s.add_points(ub + 0.5, 1.0)
     o.add_points(ub + 0.5, 1.0)
     assert relmax(s.predict(cand), o.predict(cand)) < TOL
+    assert s.handle.last_score_kernel == "dmma"
     # exact_dist and MMA_DIST = 0 take precedence
     e = pb.GpuRBFInterpolant(dim=44, lb=lb, ub=ub, exact_dist=True)
     e.add_points(X, fX)
