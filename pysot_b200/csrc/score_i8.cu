@@ -112,6 +112,13 @@ __device__ __forceinline__ void i8_tmem_ld8(uint32_t addr, uint32_t v[8]) {
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                : "r"(addr));
 }
+__device__ __forceinline__ void i8_tmem_ld16(uint32_t addr, uint32_t v[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(addr));
+}
 __device__ __forceinline__ void cp_async16_i8(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
 }
@@ -269,31 +276,29 @@ __global__ void __launch_bounds__(kI8Threads, 1) score_i8_kernel(I8Args ia) {
     double V[kI8GroupCols];
     wait_bar(&mbar);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    {
+      uint32_t v[4][kI8GroupCols];
 #pragma unroll
-    for (int c0 = 0; c0 < kI8GroupCols; c0 += 8) {
-      uint32_t v[4][8];
-#pragma unroll
-      for (int w = 0; w < 4; ++w) i8_tmem_ld8(taddr + (uint32_t)((3 + w) * kI8Cols + c0), v[w]);
+      for (int w = 0; w < 4; ++w) i8_tmem_ld16(taddr + (uint32_t)((3 + w) * kI8Cols), v[w]);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < kI8GroupCols; ++j) {
         const long long L = (long long)((int)v[0][j] * 256 + (int)v[1][j]) * 65536 + (long long)((int)v[2][j] * 256 + (int)v[3][j]);
-        V[c0 + j] = __longlong_as_double(L + 0x4338000000000000LL) - 6755399441055744.0;
+        V[j] = __longlong_as_double(L + 0x4338000000000000LL) - 6755399441055744.0;
       }
     }
     wait_bar(&mbar_free);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    {
+      uint32_t v[3][kI8GroupCols];
 #pragma unroll
-    for (int c0 = 0; c0 < kI8GroupCols; c0 += 8) {
-      uint32_t v[3][8];
-#pragma unroll
-      for (int w = 0; w < 3; ++w) i8_tmem_ld8(taddr + (uint32_t)(w * kI8Cols + c0), v[w]);
+      for (int w = 0; w < 3; ++w) i8_tmem_ld16(taddr + (uint32_t)(w * kI8Cols), v[w]);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < kI8GroupCols; ++j) {
         const long long H = (long long)(int)v[0][j] * 65536 + (long long)((int)v[1][j] * 256 + (int)v[2][j]);
         const double Hd = __longlong_as_double(H + 0x4338000000000000LL) - 6755399441055744.0;
-        V[c0 + j] = fma(Hd, 4294967296.0, V[c0 + j]);
+        V[j] = fma(Hd, 4294967296.0, V[j]);
       }
     }
     phase ^= 1;

@@ -4,7 +4,7 @@
 //   pick_kernel         : fvals[jj] = inf; winner = cand[jj]                                       (:50-51)
 //   update_kernel       : dmerit = minimum(dmerit, ||cand - winner||) + new min/max partials       (:54-55)
 // All of these are HBM-bound streaming passes over m (x d) doubles.
-#include "common.cuh"
+#include "score_kernels.cuh"
 
 namespace b200rbf {
 
@@ -281,6 +281,82 @@ __global__ void __launch_bounds__(kUpdRows) update_kernel(const double* __restri
   }
 }
 
+// The same pass with the rows brought in by TMA bulk copies (round 2).  A block of rows is CONTIGUOUS in memory, so one
+// cp.async.bulk per block (~50 KB) into a two-stage ring replaces the per-warp row loads: the first version kept ~6 KB of
+// loads in flight per SM and reached 1.0 TB/s, 15 % of the HBM peak; Little's law asks for ~45 KB.  Needs 16-byte
+// granularity: even d.  Same arithmetic and summation order as update_kernel.
+template <bool EXACT>
+__global__ void __launch_bounds__(kUpdRows) update_bulk_kernel(const double* __restrict__ cand, long long m, int d,
+                                                               const double* __restrict__ winner,
+                                                               double* __restrict__ dmerit, double* __restrict__ parts,
+                                                               int nparts, int rpp) {
+  extern __shared__ __align__(128) double s_blk[];  // 2 x rpp x d rows, + d winner
+  double* s_win = s_blk + 2 * (size_t)rpp * d;
+  __shared__ uint64_t s_bar[2];
+  __shared__ double s_red[2][kUpdRows / 32];
+  const int tid = threadIdx.x;
+  const long long nblk = (m + rpp - 1) / rpp;
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    fence_barrier_init();
+  }
+  for (int k = tid; k < d; k += blockDim.x) s_win[k] = winner[k];
+  __syncthreads();
+  auto issue = [&](long long b, int st) {
+    const long long base = b * rpp;
+    const long long rows = min((long long)rpp, m - base);
+    const uint32_t bytes = (uint32_t)(rows * d * 8);
+    mbar_expect_tx(&s_bar[st], bytes);
+    tma_bulk_g2s(s_blk + (size_t)st * rpp * d, cand + base * d, bytes, &s_bar[st]);
+  };
+  if (tid == 0) {
+    if ((long long)blockIdx.x < nblk) issue(blockIdx.x, 0);
+    if ((long long)blockIdx.x + gridDim.x < nblk) issue((long long)blockIdx.x + gridDim.x, 1);
+  }
+  double dmn = d_inf(), dmx = -d_inf();
+  int it = 0;
+  for (long long b = blockIdx.x; b < nblk; b += gridDim.x, ++it) {
+    const int st = it & 1;
+    const long long base = b * rpp;
+    const long long rows = min((long long)rpp, m - base);
+    mbar_wait(&s_bar[st], (uint32_t)((it >> 1) & 1));
+    if (tid < rows) {
+      const double* rp = s_blk + (size_t)st * rpp * d + (size_t)tid * d;
+      double acc = 0.0;
+      for (int k = 0; k < d; ++k) {
+        const double t = rp[k] - s_win[k];
+        acc = EXACT ? __dadd_rn(acc, __dmul_rn(t, t)) : fma(t, t, acc);
+      }
+      const double nd = fmin(dmerit[base + tid], sqrt(acc));
+      dmerit[base + tid] = nd;
+      dmn = fmin(dmn, nd);
+      dmx = fmax(dmx, nd);
+    }
+    __syncthreads();  // the stage is free again
+    const long long nb = b + 2 * (long long)gridDim.x;
+    if (tid == 0 && nb < nblk) issue(nb, st);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    dmn = fmin(dmn, __shfl_xor_sync(0xffffffffu, dmn, o));
+    dmx = fmax(dmx, __shfl_xor_sync(0xffffffffu, dmx, o));
+  }
+  if ((tid & 31) == 0) {
+    s_red[0][tid >> 5] = dmn;
+    s_red[1][tid >> 5] = dmx;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < kUpdRows / 32; ++w) {
+      dmn = fmin(dmn, s_red[0][w]);
+      dmx = fmax(dmx, s_red[1][w]);
+    }
+    parts[2 * nparts + blockIdx.x] = dmn;
+    parts[3 * nparts + blockIdx.x] = dmx;
+  }
+}
+
 }  // namespace
 
 int launch_stats(b200rbf_ctx* h, const double* parts, int stride, int count, int which, double* stats) {
@@ -339,6 +415,25 @@ int launch_take(b200rbf_ctx* h, const double* cand, int d, long long idx, double
 
 int launch_update(b200rbf_ctx* h, const double* cand, long long m, int d, const double* winner, double* dmerit,
                   double* parts, int stride, int* count_out, bool exact) {
+  if (d % 2 == 0 && (reinterpret_cast<uintptr_t>(cand) & 15) == 0 && m >= 4096) {
+    // rows per block: 2 stages x rows x d doubles in ~100 KB (2 CTAs per SM), at most one row per thread
+    int rpp = (int)((100 * 1024 / sizeof(double) - d) / (2 * (size_t)d));
+    if (rpp > kUpdRows) rpp = kUpdRows;
+    if (rpp >= 8) {
+      const long long want = (m + rpp - 1) / rpp;
+      const long long cap = (long long)h->sm_count * 2;
+      int blocks = (int)(want < cap ? want : cap);
+      if (blocks > stride) blocks = stride;
+      const size_t smem = (2 * (size_t)rpp * d + d) * sizeof(double);
+      auto kern = exact ? update_bulk_kernel<true> : update_bulk_kernel<false>;
+      B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<blocks, kUpdRows, smem, h->stream>>>(cand, m, d, winner, dmerit, parts, stride, rpp);
+      h->launches++;
+      B2_CUDA(cudaGetLastError());
+      *count_out = blocks;
+      return 0;
+    }
+  }
   // rows per pass: as many as fit in ~96 KB of shared memory (2 CTAs per SM), at most kUpdRows
   int rpp = (int)((96 * 1024 / sizeof(double) - d) / (size_t)(d | 1));
   if (rpp > kUpdRows) rpp = kUpdRows;
