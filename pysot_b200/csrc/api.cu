@@ -198,9 +198,11 @@ int block_rows(int dpad) {
 }
 bool use_mma(const b200rbf_ctx* h, bool with_phi);
 bool use_i8(const b200rbf_ctx* h, bool with_phi) {
-  // auto (-1): from d = 40 on the int8 kernel beats the DMMA kernel (1.03x at 40, 1.28x at 50, 1.42x at 64) and, above
-  // d = 64, the direct kernel that was the only one there (8x at 96, 15x at 128); tools/i8_sweep.py
-  const bool want = h->i8_dist == 1 || (h->i8_dist < 0 && h->model.d >= 40);
+  // auto (-1): where the int8 kernel beats the DMMA kernel -- one 32-byte k-step: d = 28 .. 32 (1.18x at 32); two and more:
+  // from d = 36 (1.02x; 1.24x at 48, 1.54x at 64) -- and, above d = 64, the direct kernel that was the only one there (8x at
+  // 96, 15x at 128); tools/i8_sweep.py, profiles/r02_i8_probes.txt
+  const int dd = h->model.d;
+  const bool want = h->i8_dist == 1 || (h->i8_dist < 0 && (dd >= 36 || (dd >= 28 && dd <= 32)));
   return with_phi && want && h->mma_dist && !h->i8_veto && !h->model.i8_bad && !h->exact_dist && h->model.d <= 128;
 }
 // candidates per CTA of the kernel that computes surrogate values / of the distance-only kernel
