@@ -68,7 +68,7 @@ enum {
   /* 1 (default): a Cholesky fit of n <= 8192 points pre-allocates room for 2 n (at least 1024) so that b200rbf_extend
    *    can append points in place; 0: never keep an extendable factorisation                                      */
   B200RBF_OPT_INCREMENTAL = 8,
-  /* -1 (default) auto = dim 28 .. 32 and from dim 36 on, 1 = always, 0 = never: the dot products of the norm expansion run on the INT8
+  /* -1 (default) auto = dim 28 .. 32 and 36 .. 64 for calls of >= 8192 rows, dim 65 .. 128 always; 1 = always, 0 = never: the dot products of the norm expansion run on the INT8
    *    tensor cores (tcgen05.mma.kind::i8, accumulators in TMEM): unit-box coordinates are 46-bit fixed-point numbers split
    *    into six base-256 digit planes, the digit products of equal weight accumulate exactly in int32 (score_i8.cu; error
    *    in r^2 below that of the FP64 norm expansion).  A call whose coordinates leave [0, 1] is re-run on the FP64 tensor

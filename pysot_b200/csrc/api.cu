@@ -201,8 +201,11 @@ bool use_i8(const b200rbf_ctx* h, bool with_phi) {
   // auto (-1): where the int8 kernel beats the DMMA kernel -- one 32-byte k-step: d = 28 .. 32 (1.18x at 32); two and more:
   // from d = 36 (1.02x; 1.24x at 48, 1.54x at 64) -- and, above d = 64, the direct kernel that was the only one there (8x at
   // 96, 15x at 128); tools/i8_sweep.py, profiles/r02_i8_probes.txt
+  // Few candidates (a strategy's 100 d per proposal) leave most SMs without a CTA of 128 rows and pay the per-CTA set-up
+  // (digit planes, TMEM allocation): below 8192 rows the DMMA kernel stays (config #2 replay: 1.14 s against 1.33 s).
   const int dd = h->model.d;
-  const bool want = h->i8_dist == 1 || (h->i8_dist < 0 && (dd >= 36 || (dd >= 28 && dd <= 32)));
+  const bool want = h->i8_dist == 1 ||
+                    (h->i8_dist < 0 && (dd > 64 || (h->cur_m >= 8192 && (dd >= 36 || (dd >= 28 && dd <= 32)))));
   return with_phi && want && h->mma_dist && !h->i8_veto && !h->model.i8_bad && !h->exact_dist && h->model.d <= 128;
 }
 // candidates per CTA of the kernel that computes surrogate values / of the distance-only kernel
@@ -717,6 +720,7 @@ static int predict_impl(b200rbf_handle h, const double* x, long long m, const do
   B2_CHECK(m >= 0, B200RBF_EINVAL, "negative row count");
   if (m == 0) return 0;
   B2_CUDA(cudaSetDevice(h->device));
+  h->cur_m = m;
   const Model& M = h->model;
   B2_TRY(upload_box(h, lb, ub, M.d, M.dpad, h->tmp_box, nullptr, nullptr));
   const bool host_in = ptr_kind(x) != kDevice, host_out = ptr_kind(out) != kDevice;
@@ -793,6 +797,7 @@ static int score_impl(b200rbf_handle h, const double* cand, long long m, const d
   B2_CHECK(m >= 1, B200RBF_EINVAL, "need at least one candidate");
   B2_CHECK(ndist >= 1, B200RBF_EINVAL, "need at least one evaluated or pending point");
   B2_CUDA(cudaSetDevice(h->device));
+  h->cur_m = m;
   const Model& M = h->model;
   ScoreState& S = h->score;
   S.valid = false;

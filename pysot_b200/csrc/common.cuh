@@ -242,6 +242,7 @@ struct b200rbf_ctx {
   bool exact_dist = false;
   bool mma_dist = true;  // norm-expansion distances on the FP64 tensor path (score_mma.cuh) unless exact_dist
   int i8_dist = -1;      // dot products of the norm expansion on the INT8 tensor cores (score_i8.cu): -1 auto (d >= 40), 0 off, 1 on
+  long long cur_m = 0;   // rows of the predict / score call in progress (kernel choice)
   bool i8_veto = false;  // this call fell back (coordinates outside the unit box): the DMMA kernel serves it
   long long chunk_rows = 131072;  // target rows per H2D chunk; rounded to whole waves of the score kernel
   int lu_panel = 128;

@@ -67,9 +67,11 @@ def test_int8_kernel_matches_oracle(orc, kernel, d, n):
 
 def test_auto_rule_and_fallback_outside_the_unit_box(orc):
     rng, lb, ub, X, fX, s, o = build(orc, "cubic", 44, 500, 3)
-    m = 4000
+    m = 9000  # auto mode takes the int8 kernel from 8192 rows on
     cand = lb + (ub - lb) * rng.random((m, 44))
-    s.predict(cand[:10])  # the fit and the lazy slicing of the centers happen here
+    s.predict(cand[:10])  # the fit happens here; few rows: the DMMA kernel
+    assert s.handle.last_score_kernel == "dmma"
+    s.predict(cand)       # the lazy slicing of the centers
     l0 = s.handle.launches
     p_in = s.predict(cand)  # d = 44 >= 40: the int8 kernel by default
     n_in = s.handle.launches - l0
