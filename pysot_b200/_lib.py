@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200rbf.so")
+LIB_PATH = os.environ.get("B200RBF_LIB") or os.path.join(_HERE, "libb200rbf.so")  # override: A/B runs of two builds
 
 KERNEL_CUBIC, KERNEL_TPS, KERNEL_LINEAR = 0, 1, 2
 TAIL_LINEAR, TAIL_CONSTANT = 0, 1

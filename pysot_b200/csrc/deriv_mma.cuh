@@ -79,18 +79,17 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 >= 9 ? 2 : 3)) deriv_mma_kern
   // A fragments of GEMM 1: unit-box coordinates of queries base + gid + 8 i, dimensions 4 k + tig (as score_mma_kernel)
   double afr[kMmaMB][K4];
   double nx[kMmaMB];
-  long long rows_i[kMmaMB];
 #pragma unroll
   for (int i = 0; i < kMmaMB; ++i) {
     const long long row = base + gid + 8 * i;
-    rows_i[i] = row < a.m ? row : (a.m - 1);
-    const double* src = a.x + rows_i[i] * (long long)a.d;
+    const double* src = a.x + (row < a.m ? row : a.m - 1) * (long long)a.d;
+    const bool live = row < a.m;  // rows past the end sit at the unit-box origin (no repeated near-pair work)
     double n2 = 0.0;
 #pragma unroll
     for (int k = 0; k < K4; ++k) {
       const int dim = 4 * k + tig;
       double v = 0.0;
-      if (dim < a.d) v = __ddiv_rn(__dsub_rn(__ldg(src + dim), __ldg(a.lb + dim)), __ldg(a.range + dim));  // utils.py:33
+      if (dim < a.d && live) v = __ddiv_rn(__dsub_rn(__ldg(src + dim), __ldg(a.lb + dim)), __ldg(a.range + dim));  // utils.py:33
       afr[i][k] = AUG ? -2.0 * v : v;
       n2 = fma(v, v, n2);
     }
@@ -113,7 +112,10 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 >= 9 ? 2 : 3)) deriv_mma_kern
 #pragma unroll
     for (int nb = 0; nb < ND; ++nb) G[i][nb][0] = G[i][nb][1] = 0.0;
   }
-  constexpr int kNearShiftHi = 10 << 20;  // near pairs: r^2 < 2^-10 (|u|^2 + |c|^2), tested on the high words
+  // direct recomputation only for tiny pairs, r^2 < 2^-T (|u|^2 + |c|^2), T = 20 cubic / 16 thin-plate: the expansion's
+  // absolute error E in r^2 enters a gradient term as 1.5 E (u - c) / r (cubic) or E (u - c) / r^2 (thin-plate), bounded by
+  // what pairs at the old 2^-10 threshold already contributed down to those r (score_mma.cuh has the full argument)
+  constexpr int kNearShiftHi = (KERN == B200RBF_KERNEL_TPS ? 16 : 20) << 20;
   const int swap = tig >> 1;              // pi swaps the two columns of the quads tig = 2, 3
   const int rowA = dm_pi(gid);            // center row (within an 8-block) behind GEMM 1's column gid
 
@@ -163,7 +165,9 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 >= 9 ? 2 : 3)) deriv_mma_kern
         }
       }
     }
-    if (near_any) {
+    // tiny pairs (cold, warp-uniform control flow): the quad forms the direct squared distance together
+    // (quad_exact_r2, score_mma.cuh)
+    if (__any_sync(0xffffffffu, near_any)) {
 #pragma unroll
       for (int jb = 0; jb < kMmaJB; ++jb)
 #pragma unroll
@@ -172,8 +176,17 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 >= 9 ? 2 : 3)) deriv_mma_kern
 #pragma unroll
           for (int i = 0; i < kMmaMB; ++i) {
             const int thr = AUG ? max(__double2hiint(nx[i]), __double2hiint(tn[jc])) : __double2hiint(nx[i] + tn[jc]);
-            if (__double2hiint(acc[i][jb][e]) < thr - kNearShiftHi)
-              acc[i][jb][e] = mma_exact_r2(a.x + rows_i[i] * (long long)a.d, a.d, a.lb, a.range, tp + jc * ds);
+            const bool mine = __double2hiint(acc[i][jb][e]) < thr - kNearShiftHi;
+            const unsigned bal = __ballot_sync(0xffffffffu, mine);
+            if (bal != 0u) {
+#pragma unroll 1
+              for (int src = 0; src < 4; ++src) {
+                if ((bal & (0x11111111u << src)) == 0u) continue;  // no quad has this column flagged
+                const int jsrc = 8 * jb + 2 * src + (e ^ (src >> 1));
+                const double r2x = quad_exact_r2<K4, AUG>(afr[i], a.d, tig, tp + jsrc * ds);
+                if (src == tig && mine) acc[i][jb][e] = r2x;
+              }
+            }
           }
         }
     }

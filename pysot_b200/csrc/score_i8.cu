@@ -119,6 +119,16 @@ __device__ __forceinline__ void i8_tmem_ld16(uint32_t addr, uint32_t v[16]) {
         "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(addr));
 }
+// int64 (|x| < 2^51) -> double.  B2_I8_XU_CONV = 1: the conversion instruction (XU pipe, quarter rate; measured: no faster)
+// apart from one MUFU per pair); 0: the 2^52 + 2^51 bias trick (two integer adds + one FP64 add)
+#ifndef B2_I8_XU_CONV
+#define B2_I8_XU_CONV 0
+#endif
+#if B2_I8_XU_CONV
+#define I8_CONV(x) ((double)(x))
+#else
+#define I8_CONV(x) (__longlong_as_double((x) + 0x4338000000000000LL) - 6755399441055744.0)
+#endif
 __device__ __forceinline__ void cp_async16_i8(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
 }
@@ -247,7 +257,9 @@ __global__ void __launch_bounds__(kI8Threads, 1) score_i8_kernel(I8Args ia) {
     issue_weights(t, 3, 6, &mbar);
     issue_weights(t, 0, 2, &mbar_free);
   };
+  // which pairs are recomputed directly: tiny ones and near ones that can lower the running minimum (score_mma.cuh)
   constexpr int kNearShiftHi = 10 << 20;
+  constexpr int kTinyShiftHi = (KERN == B200RBF_KERNEL_LINEAR ? 10 : KERN == B200RBF_KERNEL_TPS ? 16 : 20) << 20;
   const int q4 = warp & 3, cg = (warp >> 2) & 3;  // TMEM lane quarter = warp id within the CTA mod 4
   const int crow = 32 * q4 + lane;
   double sum = 0.0;
@@ -284,7 +296,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) score_i8_kernel(I8Args ia) {
 #pragma unroll
       for (int j = 0; j < kI8GroupCols; ++j) {
         const long long L = (long long)((int)v[0][j] * 256 + (int)v[1][j]) * 65536 + (long long)((int)v[2][j] * 256 + (int)v[3][j]);
-        V[j] = __longlong_as_double(L + 0x4338000000000000LL) - 6755399441055744.0;
+        V[j] = I8_CONV(L);
       }
     }
     wait_bar(&mbar_free);
@@ -297,8 +309,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) score_i8_kernel(I8Args ia) {
 #pragma unroll
       for (int j = 0; j < kI8GroupCols; ++j) {
         const long long H = (long long)(int)v[0][j] * 65536 + (long long)((int)v[1][j] * 256 + (int)v[2][j]);
-        const double Hd = __longlong_as_double(H + 0x4338000000000000LL) - 6755399441055744.0;
-        V[j] = fma(Hd, 4294967296.0, V[j]);
+        V[j] = fma(I8_CONV(H), 4294967296.0, V[j]);
       }
     }
     phase ^= 1;
@@ -317,36 +328,36 @@ __global__ void __launch_bounds__(kI8Threads, 1) score_i8_kernel(I8Args ia) {
 #pragma unroll
     for (int c0 = 0; c0 < kI8GroupCols; c0 += 8) {
       double r2v[8];
-      bool near_any = false;
+      // one flag per pair: tiny (direct recomputation) or may lower the running minimum -- both rare (score_mma.cuh)
+      bool flag = false;
+      const int mnhi1 = (int)(mnb >> 32) + 1;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const double sq = nu + tn[c0 + j];
         const double r2 = fma(V[c0 + j], -1.734723475976807e-18 /* 2^-59 */, sq);
-        near_any |= __double2hiint(r2) < __double2hiint(sq) - kNearShiftHi;
+        flag |= __double2hiint(r2) < max(__double2hiint(sq) - kTinyShiftHi, mnhi1);
         r2v[j] = r2;
       }
-      if (near_any) {  // rare: direct differences in the arithmetic of score_kernel (bit-identical to it)
+      if (flag) {  // rare
+        bool near_any = false;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const double sq = nu + tn[c0 + j];
-          if (__double2hiint(r2v[j]) < __double2hiint(sq) - kNearShiftHi) {
-            const int cj = t * kI8Cols + kI8GroupCols * cg + c0 + j;
-            const int cjr = cj < a.npad ? cj : a.npad - 1;
-            r2v[j] = mma_exact_r2(a.cand + grow * (long long)a.d, a.d, a.lb, a.range, a.pts + (size_t)cjr * ia.dpad);
+        for (int j = 0; j < 8; ++j) near_any |= __double2hiint(r2v[j]) < __double2hiint(nu + tn[c0 + j]) - kNearShiftHi;
+        if (near_any) {  // rarer: direct differences (the arithmetic of score_kernel) for the tiny and the near flagged pairs
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int thr = __double2hiint(nu + tn[c0 + j]);
+            if (__double2hiint(r2v[j]) < max(thr - kTinyShiftHi, min(thr - kNearShiftHi, mnhi1))) {
+              const int cj = t * kI8Cols + kI8GroupCols * cg + c0 + j;
+              const int cjr = cj < a.npad ? cj : a.npad - 1;
+              r2v[j] = mma_exact_r2(a.cand + grow * (long long)a.d, a.d, a.lb, a.range, a.pts + (size_t)cjr * ia.dpad);
+            }
           }
         }
-      }
-      bool min_any = false;
-      const int mnhi = (int)(mnb >> 32);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        min_any |= __double2hiint(r2v[j]) <= mnhi;
-        sum = fma(mma_phi_from_r2<KERN>(r2v[j], s_tps), tw[c0 + j], sum);
-      }
-      if (min_any) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) mnb = min(mnb, __double_as_longlong(r2v[j]));  // pad rows duplicate a real center
       }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum = fma(mma_phi_from_r2<KERN>(r2v[j], s_tps), tw[c0 + j], sum);
     }
   }
   // combine the column groups, write the outputs and the CTA's statistics

@@ -147,6 +147,30 @@ static __device__ __noinline__ double mma_exact_r2(const double* __restrict__ sr
   return acc;
 }
 
+// Near pairs, quad-cooperative (round 2).  The four threads of a quad hold one candidate's coordinates between them
+// (dimensions 4 k + tig), so they form the direct squared distance to a shared-memory center row together: K4 FMAs each
+// and two shuffles, instead of one thread walking all d coordinates from global memory through the unit-box division
+// (mma_exact_r2: ~500 instructions per pair).  On optimiser-like clouds -- hundreds of evaluated points within 0.1 of the
+// incumbent, exactly what SOP / DYCORS produce late in a run -- most pairs of a proposal are near pairs: predict() of one
+// point took 1.2 us PER CENTER there (3.3 ms at n = 2800, tools/replay_probe.py) against 0.05 us on a uniform cloud.
+// Same direct-difference arithmetic, coincident points still give r = 0 exactly.  The whole warp must call it (converged).
+template <int K4, bool AUG>
+__device__ __forceinline__ double quad_exact_r2(const double (&afr_i)[K4], int d, int tig, const double* __restrict__ crow) {
+  double p = 0.0;
+#pragma unroll
+  for (int k = 0; k < K4; ++k) {
+    const int dim = 4 * k + tig;
+    if (dim < d) {
+      const double u = AUG ? -0.5 * afr_i[k] : afr_i[k];  // the fragments hold -2 u (exact scaling)
+      const double t = u - crow[dim];
+      p = fma(t, t, p);
+    }
+  }
+  p += __shfl_xor_sync(0xffffffffu, p, 1);
+  p += __shfl_xor_sync(0xffffffffu, p, 2);
+  return p;
+}
+
 // AUG (usable when d + 2 <= 4 K4, i.e. d mod 4 is 1 or 2): the two unused slots of the last k-step carry the norms --
 // A row = (-2 u, |u|^2, 1), B row = (c, 1, |c|^2) -- so the MMA accumulates r^2 itself and pass 1 needs no FP64
 // instruction at all; the near test then compares against 2^-10 max(|u|^2, |c|^2) (integer max of the high words).
@@ -192,18 +216,17 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 >= 12 ? kMmaMinBlocks - 1 : k
   // A fragments: shifted unit-box coordinates of candidates base + gid + 8 i, dimensions 4 k + tig
   double afr[kMmaMB][K4];
   double nx[kMmaMB];
-  long long rows_i[kMmaMB];
 #pragma unroll
   for (int i = 0; i < kMmaMB; ++i) {
     const long long row = base + gid + 8 * i;
-    rows_i[i] = row < a.m ? row : (a.m - 1);
-    const double* src = a.cand + rows_i[i] * (long long)a.d;
-    double n2 = 0.0;
+    const double* src = a.cand + (row < a.m ? row : a.m - 1) * (long long)a.d;
+    const bool live = row < a.m;  // rows past the end compute on the unit-box origin: copies of row m - 1 would repeat
+    double n2 = 0.0;              // its near-pair work 15 times over in a one-point predict()
 #pragma unroll
     for (int k = 0; k < K4; ++k) {
       const int dim = 4 * k + tig;
       double v = 0.0;
-      if (dim < a.d) {
+      if (dim < a.d && live) {
         v = __ldg(src + dim);
         if (a.lb != nullptr) v = __ddiv_rn(__dsub_rn(v, __ldg(a.lb + dim)), __ldg(a.range + dim));
       }
@@ -230,7 +253,17 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 >= 12 ? kMmaMinBlocks - 1 : k
     sum[i] = 0.0;
     mnb[i] = 0x7ff0000000000000LL;
   }
-  constexpr int kNearShiftHi = 10 << 20;  // near pairs: r^2 < 2^-10 (|u|^2 + |c|^2), tested on the high words
+  // Which pairs are recomputed directly (round 2, after the SOP replay: on an optimiser's clustered cloud MOST pairs have
+  // r^2 < 2^-10 (|u|^2 + |c|^2), and recomputing all of them made the exception the rule).  The norm expansion's absolute
+  // error in r^2 is E ~ 3 eps (|u|^2 + |c|^2) whatever r is, so for the kernel SUM a close pair is no worse than a far
+  // one: d(r^3) = 1.5 r E shrinks with r, d(r^2 log r) grows only like |log r|.  Direct recomputation is needed for
+  //  * tiny pairs, r^2 < 2^-T (|u|^2 + |c|^2): coincident points must give r = 0 exactly, the TPS log and the linear
+  //    kernel's sqrt amplify the relative error there (T = 20 cubic, 16 thin-plate, 10 linear = the old rule);
+  //  * near pairs (2^-10) that can lower the running minimum: dmerit must be exact relative to ITSELF.  The test is on
+  //    the high words (hi(r2) <= hi(min)), which leaves 2^-20 of slack against E / r^2 <= 3e-13 * 2^10 for non-tiny pairs.
+  // A near pair that is neither keeps its expanded r^2: it cannot be the minimum and its kernel value is accurate.
+  constexpr int kNearShiftHi = 10 << 20;
+  constexpr int kTinyShiftHi = (KERN == B200RBF_KERNEL_LINEAR ? 10 : KERN == B200RBF_KERNEL_TPS ? 16 : 20) << 20;
 
   for (int t = 0; t < ntiles; ++t) {
     const int s = t % kMmaStages;
@@ -262,7 +295,16 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 >= 12 ? kMmaMinBlocks - 1 : k
       // The near test r2 < 2^-10 sq runs on the INTEGER pipe (the FP64 pipe is the bottleneck) and on the high words
       // only: for non-negative doubles the bit patterns order like the values, 2^-10 sq is sq with its exponent
       // lowered by 10, and a negative r2 (cancellation) is a negative integer, i.e. below any threshold.
-      bool near_any = false;
+      // One flag per pair, two integer instructions: hi(r2) < max(hi(thr) - T, hi(min) + 1), i.e. "tiny, or may lower the
+      // running minimum" -- both rare (a row's minimum is lowered O(log n) times over a sweep), so the block below is
+      // cold on uniform and clustered clouds alike.
+      bool flag = false;
+      int pmn[kMmaMB];  // max(hi(|u|^2) - T, hi(min) + 1): the per-row half of the threshold
+#pragma unroll
+      for (int i = 0; i < kMmaMB; ++i) {
+        const int m1 = (int)(mnb[i] >> 32) + 1;
+        pmn[i] = AUG ? max(__double2hiint(nx[i]) - kTinyShiftHi, m1) : m1;
+      }
 #pragma unroll
       for (int jb = 0; jb < kMmaJB; ++jb) {
         const double2 n2 = *reinterpret_cast<const double2*>(tn + j0 + 8 * jb + 2 * tig);
@@ -271,61 +313,78 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 >= 12 ? kMmaMinBlocks - 1 : k
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             if (AUG) {
-              near_any |= __double2hiint(acc[i][jb][e]) <
-                          max(__double2hiint(nx[i]), __double2hiint(e ? n2.y : n2.x)) - kNearShiftHi;
+              flag |= __double2hiint(acc[i][jb][e]) < max(__double2hiint(e ? n2.y : n2.x) - kTinyShiftHi, pmn[i]);
             } else {
               const double sq = nx[i] + (e ? n2.y : n2.x);
-              const double r2 = fma(-2.0, acc[i][jb][e], sq);
-              near_any |= __double2hiint(r2) < __double2hiint(sq) - kNearShiftHi;
-              acc[i][jb][e] = r2;
+              acc[i][jb][e] = fma(-2.0, acc[i][jb][e], sq);
+              flag |= __double2hiint(acc[i][jb][e]) < max(__double2hiint(sq) - kTinyShiftHi, pmn[i]);
             }
           }
         }
       }
-      // (2) rare: recompute the near pairs directly (same arithmetic as score_kernel, so they are bit-identical to it)
-      if (near_any) {
+      // (2) cold, warp-uniform control flow (every shuffle below runs converged): direct recomputation of the flagged
+      // pairs that are tiny or near -- the quad works together on each (quad_exact_r2) -- then the exact update of the
+      // running minimum, shared across the quad (four times fewer "new minimum" events than per-thread minima, and
+      // with them four times fewer entries into this block: ~12 % of the steps at n = 20 000)
+      if (__any_sync(0xffffffffu, flag)) {
+        bool rec = false;
 #pragma unroll
         for (int jb = 0; jb < kMmaJB; ++jb) {
-          const int jc = j0 + 8 * jb + 2 * tig;
+          const double2 n2 = *reinterpret_cast<const double2*>(tn + j0 + 8 * jb + 2 * tig);
 #pragma unroll
           for (int i = 0; i < kMmaMB; ++i) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-              const int thr = AUG ? max(__double2hiint(nx[i]), __double2hiint(tn[jc + e]))
-                                  : __double2hiint(nx[i] + tn[jc + e]);
-              if (__double2hiint(acc[i][jb][e]) < thr - kNearShiftHi)
-                acc[i][jb][e] = mma_exact_r2(a.cand + rows_i[i] * (long long)a.d, a.d, a.lb, a.range, tp + (jc + e) * ds);
+              const double cn = e ? n2.y : n2.x;
+              const int thr = AUG ? max(__double2hiint(nx[i]), __double2hiint(cn)) : __double2hiint(nx[i] + cn);
+              rec |= __double2hiint(acc[i][jb][e]) < thr - kNearShiftHi;  // superset of the test below, cheaper
             }
           }
         }
-      }
-      // (3) the weighted kernel sum, same summation order as before; the running minimum only pre-tests the high
-      // words here (one integer compare per pair, r2 >= 0 so the bit patterns order like the values) ...
-      bool min_any = false;
-      int mnhi[kMmaMB];
+        if (__any_sync(0xffffffffu, rec)) {
 #pragma unroll
-      for (int i = 0; i < kMmaMB; ++i) mnhi[i] = (int)(mnb[i] >> 32);
+          for (int jb = 0; jb < kMmaJB; ++jb) {
+            const double2 n2 = *reinterpret_cast<const double2*>(tn + j0 + 8 * jb + 2 * tig);
+#pragma unroll
+            for (int i = 0; i < kMmaMB; ++i) {
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const double cn = e ? n2.y : n2.x;
+                const int thr = AUG ? max(__double2hiint(nx[i]), __double2hiint(cn)) : __double2hiint(nx[i] + cn);
+                const bool mine = __double2hiint(acc[i][jb][e]) <
+                                  max(thr - kTinyShiftHi, min(thr - kNearShiftHi, (int)(mnb[i] >> 32) + 1));
+                const unsigned bal = __ballot_sync(0xffffffffu, mine);
+                if (bal != 0u) {
+#pragma unroll 1
+                  for (int src = 0; src < 4; ++src) {
+                    if ((bal & (0x11111111u << src)) == 0u) continue;  // no quad has this column flagged
+                    const double r2x = quad_exact_r2<K4, AUG>(afr[i], a.d, tig, tp + (j0 + 8 * jb + 2 * src + e) * ds);
+                    if (src == tig && mine) acc[i][jb][e] = r2x;
+                  }
+                }
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < kMmaMB; ++i) {
+#pragma unroll
+          for (int jb = 0; jb < kMmaJB; ++jb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) mnb[i] = min(mnb[i], __double_as_longlong(acc[i][jb][e]));
+          mnb[i] = min(mnb[i], __shfl_xor_sync(0xffffffffu, mnb[i], 1));
+          mnb[i] = min(mnb[i], __shfl_xor_sync(0xffffffffu, mnb[i], 2));
+        }
+      }
+      // (3) the weighted kernel sum, same summation order as before
 #pragma unroll
       for (int jb = 0; jb < kMmaJB; ++jb) {
         const double2 w2 = *reinterpret_cast<const double2*>(tw + j0 + 8 * jb + 2 * tig);
 #pragma unroll
         for (int i = 0; i < kMmaMB; ++i) {
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const double r2 = acc[i][jb][e];
-            min_any |= __double2hiint(r2) <= mnhi[i];
-            sum[i] = fma(mma_phi_from_r2<KERN>(r2, s_tps), e ? w2.y : w2.x, sum[i]);
-          }
+          for (int e = 0; e < 2; ++e) sum[i] = fma(mma_phi_from_r2<KERN>(acc[i][jb][e], s_tps), e ? w2.y : w2.x, sum[i]);
         }
-      }
-      // ... (4) and is updated exactly only when some pair can lower it (ever rarer as the sweep proceeds)
-      if (min_any) {
-#pragma unroll
-        for (int jb = 0; jb < kMmaJB; ++jb)
-#pragma unroll
-          for (int i = 0; i < kMmaMB; ++i)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) mnb[i] = min(mnb[i], __double_as_longlong(acc[i][jb][e]));
       }
     }
     __syncthreads();
