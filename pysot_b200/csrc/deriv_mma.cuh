@@ -112,10 +112,10 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 >= 9 ? 2 : 3)) deriv_mma_kern
 #pragma unroll
     for (int nb = 0; nb < ND; ++nb) G[i][nb][0] = G[i][nb][1] = 0.0;
   }
-  // direct recomputation only for tiny pairs, r^2 < 2^-T (|u|^2 + |c|^2), T = 20 cubic / 16 thin-plate: the expansion's
-  // absolute error E in r^2 enters a gradient term as 1.5 E (u - c) / r (cubic) or E (u - c) / r^2 (thin-plate), bounded by
-  // what pairs at the old 2^-10 threshold already contributed down to those r (score_mma.cuh has the full argument)
-  constexpr int kNearShiftHi = (KERN == B200RBF_KERNEL_TPS ? 16 : 20) << 20;
+  // direct recomputation only for tiny pairs, r^2 < 2^-T (|u|^2 + |c|^2): the expansion's absolute error E in r^2 enters
+  // a cubic gradient term as 1.5 w E (u - c)_k / r <= 1.5 w E whatever r is (T = 40: duplicates and negative r^2 only),
+  // a thin-plate one as w E (u - c)_k / r^2 <= w E / r (T = 16: 3e-13 w at the threshold); score_mma.cuh has the argument
+  constexpr int kNearShiftHi = (KERN == B200RBF_KERNEL_TPS ? 16 : 40) << 20;
   const int swap = tig >> 1;              // pi swaps the two columns of the quads tig = 2, 3
   const int rowA = dm_pi(gid);            // center row (within an 8-block) behind GEMM 1's column gid
 

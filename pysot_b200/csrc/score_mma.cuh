@@ -256,14 +256,16 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 >= 12 ? kMmaMinBlocks - 1 : k
   // Which pairs are recomputed directly (round 2, after the SOP replay: on an optimiser's clustered cloud MOST pairs have
   // r^2 < 2^-10 (|u|^2 + |c|^2), and recomputing all of them made the exception the rule).  The norm expansion's absolute
   // error in r^2 is E ~ 3 eps (|u|^2 + |c|^2) whatever r is, so for the kernel SUM a close pair is no worse than a far
-  // one: d(r^3) = 1.5 r E shrinks with r, d(r^2 log r) grows only like |log r|.  Direct recomputation is needed for
-  //  * tiny pairs, r^2 < 2^-T (|u|^2 + |c|^2): coincident points must give r = 0 exactly, the TPS log and the linear
-  //    kernel's sqrt amplify the relative error there (T = 20 cubic, 16 thin-plate, 10 linear = the old rule);
+  // one: d(r^3) = 1.5 r E shrinks with r, d(r^2 log r) = E (log r + 1/2) grows only like |log r| (17 E at r = 1e-7; a
+  // coincident pair contributes ~1e-14 w instead of 0).  Direct recomputation is needed for
+  //  * tiny pairs, r^2 < 2^-T (|u|^2 + |c|^2), T = 40: in effect duplicates, and every pair whose expanded r^2 came out
+  //    negative (a negative double is a negative integer, below any threshold) -- sqrt must not see those.  The linear
+  //    kernel keeps T = 10, the old rule: d(r) = E / (2 r) is unbounded;
   //  * near pairs (2^-10) that can lower the running minimum: dmerit must be exact relative to ITSELF.  The test is on
   //    the high words (hi(r2) <= hi(min)), which leaves 2^-20 of slack against E / r^2 <= 3e-13 * 2^10 for non-tiny pairs.
   // A near pair that is neither keeps its expanded r^2: it cannot be the minimum and its kernel value is accurate.
   constexpr int kNearShiftHi = 10 << 20;
-  constexpr int kTinyShiftHi = (KERN == B200RBF_KERNEL_LINEAR ? 10 : KERN == B200RBF_KERNEL_TPS ? 16 : 20) << 20;
+  constexpr int kTinyShiftHi = (KERN == B200RBF_KERNEL_LINEAR ? 10 : 40) << 20;
 
   for (int t = 0; t < ntiles; ++t) {
     const int s = t % kMmaStages;
