@@ -208,11 +208,18 @@ bool use_i8(const b200rbf_ctx* h, bool with_phi) {
                     (h->i8_dist < 0 && (dd > 64 || (h->cur_m >= 8192 && (dd >= 36 || (dd >= 28 && dd <= 32)))));
   return with_phi && want && h->mma_dist && !h->i8_veto && !h->model.i8_bad && !h->exact_dist && h->model.d <= 128;
 }
+// DMMA score kernel, few candidates: 2 or 4 warps share a 16-row group and split the centers between them, so that a
+// strategy-sized call (100 d candidates) fills the SMs: 16-row groups x split <= ~1 CTA slot in 3 per SM
+int mma_split(const b200rbf_ctx* h) {
+  const long long groups = (h->cur_m + 8 * kMmaMB - 1) / (8 * kMmaMB);
+  const long long warps = (long long)h->sm_count * 12;
+  return groups * 4 <= warps ? 4 : groups * 2 <= warps ? 2 : 1;
+}
 // candidates per CTA of the kernel that computes surrogate values / of the distance-only kernel
 int main_rows(const b200rbf_ctx* h) {
   if (use_i8(h, true)) return i8_rows_per_cta();
   if (h->model.dpad > kMaxRegDim) return score_generic_threads();
-  return use_mma(h, true) ? kMmaRowsPerCta : kScoreThreads;
+  return use_mma(h, true) ? kMmaRowsPerCta / mma_split(h) : kScoreThreads;
 }
 int dist_rows(const b200rbf_ctx* h) { return h->model.dpad > kMaxRegDim ? score_generic_threads() : kScoreThreads; }
 
@@ -233,6 +240,7 @@ int launch_score_mma(b200rbf_ctx* h, const ScoreArgs& a) {
   ma.s.pts = M.aug ? M.centers_m.as<double>() : M.centers_x.as<double>();
   ma.cnorm = M.cnorm.as<double>();
   ma.ds = M.ds;
+  ma.split = a.occ_out != nullptr ? 1 : mma_split(h);
   const int k4 = (M.d + 3) / 4;
   switch ((k4 - 1) / 4) {
     case 0: return launch_score_mma_group0(h, ma, k4, M.kernel);

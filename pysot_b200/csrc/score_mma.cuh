@@ -45,6 +45,7 @@ static_assert(B2_PAD_ROWS % kMmaTileRows == 0, "pad_rows() pads the center rows 
 #endif
 constexpr int kMmaStages = B2_MMA_STAGES;
 constexpr int kMmaRowsPerCta = (kMmaThreads / 32) * 8 * kMmaMB;
+constexpr int kMmaPartDoubles = 2 * (kMmaThreads / 32) * 8 * kMmaMB;  // per-warp partial sums and minima (center split)
 
 struct MmaArgs {
   ScoreArgs s;          // pts = shifted centers (npad x ds), coef = weights, as in score_kernel
@@ -52,6 +53,7 @@ struct MmaArgs {
   bool aug;             // centers carry (1, |c|^2) in slots d, d + 1 (see score_mma_kernel)
   const double2* tps_table;  // kTpsLogEntries x (inv_j, -0.5 log inv_j), device memory (thin-plate spline only)
   int ds;               // center row stride in doubles (== 4 mod 16, >= 4 * K4)
+  int split;            // 1, 2 or 4 warps share one 16-row group and take every split-th center tile (few candidates)
 };
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
@@ -179,13 +181,15 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 >= 12 ? kMmaMinBlocks - 1 : k
   const ScoreArgs& a = ma.s;
   const int ds = ma.ds;
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int trows = kMmaTileRows * ma.split;  // center rows per stage: one 32-row tile per warp of a row group
   double* s_pts = reinterpret_cast<double*>(smem_raw);                    // [stages][rows * ds]
-  double* s_wts = s_pts + (size_t)kMmaStages * kMmaTileRows * ds;          // [stages][rows]
-  double* s_nrm = s_wts + kMmaStages * kMmaTileRows;                       // [stages][rows]
-  uint64_t* s_full = reinterpret_cast<uint64_t*>(s_nrm + kMmaStages * kMmaTileRows);
+  double* s_wts = s_pts + (size_t)kMmaStages * trows * ds;          // [stages][rows]
+  double* s_nrm = s_wts + kMmaStages * trows;                       // [stages][rows]
+  uint64_t* s_full = reinterpret_cast<uint64_t*>(s_nrm + kMmaStages * trows);
   double* s_red = reinterpret_cast<double*>(s_full + kMmaStages);         // 4 x warps
-  // thin-plate spline only: the half-log table (2 KB), 16-byte aligned behind the reduction scratch
-  const double2* s_tps = reinterpret_cast<const double2*>(s_red + 4 * (kMmaThreads / 32) + (kMmaStages & 1));
+  double* s_part = s_red + 4 * (kMmaThreads / 32);                         // center split: warps x 16 rows x (sum, min)
+  // thin-plate spline only: the half-log table (2 KB), 16-byte aligned behind the scratch
+  const double2* s_tps = reinterpret_cast<const double2*>(s_part + kMmaPartDoubles + (kMmaStages & 1));
   if (KERN == B200RBF_KERNEL_TPS) {
     double2* dst = const_cast<double2*>(s_tps);
     for (int i = threadIdx.x; i < kTpsLogEntries; i += kMmaThreads) dst[i] = ma.tps_table[i];
@@ -193,8 +197,12 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 >= 12 ? kMmaMinBlocks - 1 : k
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gid = lane >> 2, tig = lane & 3;
-  const long long base = ((long long)blockIdx.x * (kMmaThreads / 32) + warp) * (8 * kMmaMB);
-  const int ntiles = (a.npad + kMmaTileRows - 1) / kMmaTileRows;
+  // Center split (few candidates: a strategy's 100 d per proposal would occupy m / 64 CTAs, a fraction of the SMs, and
+  // predict() of one point a single warp): `split` warps share a row group, a stage holds `split` 32-row tiles and warp
+  // `sub` of the group takes tile `sub` of every stage; the partial sums / minima are combined in a fixed order at the end.
+  const int sub = warp & (ma.split - 1);
+  const long long base = ((long long)blockIdx.x * ((kMmaThreads / 32) / ma.split) + warp / ma.split) * (8 * kMmaMB);
+  const int ntiles = (a.npad + trows - 1) / trows;
 
   if (tid == 0) {
     for (int s = 0; s < kMmaStages; ++s) mbar_init(&s_full[s], 1);
@@ -203,12 +211,12 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 >= 12 ? kMmaMinBlocks - 1 : k
   __syncthreads();
   auto issue = [&](int t) {
     const int s = t % kMmaStages;
-    const int r0 = t * kMmaTileRows;
-    const int rows = min(kMmaTileRows, a.npad - r0);
+    const int r0 = t * trows;
+    const int rows = min(trows, a.npad - r0);
     mbar_expect_tx(&s_full[s], (uint32_t)rows * (uint32_t)(ds * 8 + 16));
-    tma_bulk_g2s(s_pts + (size_t)s * kMmaTileRows * ds, a.pts + (size_t)r0 * ds, (uint32_t)rows * ds * 8u, &s_full[s]);
-    tma_bulk_g2s(s_wts + s * kMmaTileRows, a.coef + r0, rows * 8u, &s_full[s]);
-    tma_bulk_g2s(s_nrm + s * kMmaTileRows, ma.cnorm + r0, rows * 8u, &s_full[s]);
+    tma_bulk_g2s(s_pts + (size_t)s * trows * ds, a.pts + (size_t)r0 * ds, (uint32_t)rows * ds * 8u, &s_full[s]);
+    tma_bulk_g2s(s_wts + s * trows, a.coef + r0, rows * 8u, &s_full[s]);
+    tma_bulk_g2s(s_nrm + s * trows, ma.cnorm + r0, rows * 8u, &s_full[s]);
   };
   if (tid == 0)
     for (int t = 0; t < kMmaStages && t < ntiles; ++t) issue(t);
@@ -269,12 +277,13 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 >= 12 ? kMmaMinBlocks - 1 : k
 
   for (int t = 0; t < ntiles; ++t) {
     const int s = t % kMmaStages;
-    const int rows = min(kMmaTileRows, a.npad - t * kMmaTileRows);  // always a full tile (see pad_rows)
+    const int rows = min(trows, a.npad - t * trows);  // always a full tile (see pad_rows)
     mbar_wait(&s_full[s], (uint32_t)((t / kMmaStages) & 1));
-    const double* tp = s_pts + (size_t)s * kMmaTileRows * ds;
-    const double* tw = s_wts + s * kMmaTileRows;
-    const double* tn = s_nrm + s * kMmaTileRows;
-    for (int j0 = 0; j0 < rows; j0 += 8 * kMmaJB) {  // npad is a multiple of 32 = 8 kMmaJB: tiles are always full
+    const double* tp = s_pts + (size_t)s * trows * ds;
+    const double* tw = s_wts + s * trows;
+    const double* tn = s_nrm + s * trows;
+    if (base < a.m)
+    for (int j0 = 8 * kMmaJB * sub; j0 < rows; j0 += trows) {  // npad is a multiple of 32 = 8 kMmaJB: tiles are always full
       double acc[kMmaMB][kMmaJB][2];
 #pragma unroll
       for (int i = 0; i < kMmaMB; ++i)
@@ -401,6 +410,26 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 >= 12 ? kMmaMinBlocks - 1 : k
     mnb[i] = min(mnb[i], __shfl_xor_sync(0xffffffffu, mnb[i], 1));
     mnb[i] = min(mnb[i], __shfl_xor_sync(0xffffffffu, mnb[i], 2));
   }
+  if (ma.split > 1) {  // combine the warps of a row group: sub 0 adds the others' partial results, in order
+    long long* s_pmin = reinterpret_cast<long long*>(s_part + kMmaPartDoubles / 2);
+    if (tig == 0) {
+#pragma unroll
+      for (int i = 0; i < kMmaMB; ++i) {
+        s_part[warp * (8 * kMmaMB) + gid + 8 * i] = sum[i];
+        s_pmin[warp * (8 * kMmaMB) + gid + 8 * i] = mnb[i];
+      }
+    }
+    __syncthreads();
+    if (sub == 0) {
+      for (int o = 1; o < ma.split; ++o) {
+#pragma unroll
+        for (int i = 0; i < kMmaMB; ++i) {
+          sum[i] += s_part[(warp + o) * (8 * kMmaMB) + gid + 8 * i];
+          mnb[i] = min(mnb[i], s_pmin[(warp + o) * (8 * kMmaMB) + gid + 8 * i]);
+        }
+      }
+    }
+  }
   // tail: lambda_0 + sum_k lambda_k u_k over this thread's dimensions, then across the quad
   double fmn = inf, fmx = -inf, dmn = inf, dmx = -inf;
 #pragma unroll
@@ -417,7 +446,7 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 >= 12 ? kMmaMinBlocks - 1 : k
     ts += __shfl_xor_sync(0xffffffffu, ts, 2);
     if (AUG) ts *= -0.5;  // the fragments hold -2 u (exact scaling)
     const long long row = base + gid + 8 * i;
-    const bool live = row < a.m;
+    const bool live = row < a.m && sub == 0;
     const double fval = sum[i] + (ts + __ldg(a.tailc));
     double dval = 0.0;
     if (a.min_mode != 0) dval = a.dscale * sqrt(__longlong_as_double(mnb[i]));
@@ -465,21 +494,23 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 >= 12 ? kMmaMinBlocks - 1 : k
   }
 }
 
-inline size_t score_mma_smem_bytes(int ds, bool tps = false) {
-  return ((size_t)kMmaStages * kMmaTileRows * ds + 2 * (size_t)kMmaStages * kMmaTileRows + kMmaStages +
-          4 * (kMmaThreads / 32) + (tps ? 2 * kTpsLogEntries + 1 : 0)) * 8;
+inline size_t score_mma_smem_bytes(int ds, bool tps = false, int split = 1) {
+  const size_t trows = (size_t)kMmaTileRows * split;
+  return ((size_t)kMmaStages * trows * ds + 2 * (size_t)kMmaStages * trows + kMmaStages +
+          4 * (kMmaThreads / 32) + kMmaPartDoubles + (tps ? 2 * kTpsLogEntries + 1 : 0)) * 8;
 }
 
 template <int K4, int KERN, bool AUG>
 int launch_score_mma_inst(b200rbf_ctx* h, const MmaArgs& ma) {
   auto kern = score_mma_kernel<K4, KERN, AUG>;
-  const size_t smem = score_mma_smem_bytes(ma.ds, KERN == B200RBF_KERNEL_TPS);
+  const size_t smem = score_mma_smem_bytes(ma.ds, KERN == B200RBF_KERNEL_TPS, ma.split);
   B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (ma.s.occ_out != nullptr) {
     B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(ma.s.occ_out, kern, kMmaThreads, smem));
     return 0;
   }
-  const long long blocks = (ma.s.m + kMmaRowsPerCta - 1) / kMmaRowsPerCta;
+  const int rows_per_cta = kMmaRowsPerCta / ma.split;
+  const long long blocks = (ma.s.m + rows_per_cta - 1) / rows_per_cta;
   kern<<<(unsigned)blocks, kMmaThreads, smem, h->stream>>>(ma);
   h->launches++;
   B2_CUDA(cudaGetLastError());

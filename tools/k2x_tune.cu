@@ -43,7 +43,7 @@ int main(int argc, char** argv) {
   ScoreArgs& a = ma.s;
   a.cand = cand; a.m = m; a.d = d; a.lb = box; a.range = box + pad_dim(d); a.pts = pts; a.coef = coef; a.tailc = tailc;
   a.npad = npad; a.tail = 0; a.dscale = 1.0; a.min_mode = 1; a.fvals = fv; a.dmerit = dm; a.parts = parts; a.nparts = nparts;
-  ma.cnorm = nrm; ma.ds = ds; ma.aug = TUNE_AUG;
+  ma.cnorm = nrm; ma.ds = ds; ma.aug = TUNE_AUG; ma.split = 1;
   { std::vector<double> ht2(2 * kTpsLogEntries); tps_log_table_host(ht2.data()); double* tt; CK(cudaMalloc(&tt, ht2.size() * 8)); CK(cudaMemcpy(tt, ht2.data(), ht2.size() * 8, cudaMemcpyHostToDevice)); ma.tps_table = reinterpret_cast<const double2*>(tt); }
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   auto run = [&]() { return launch_score_mma_inst<K4, TUNE_KERN, TUNE_AUG>(&ctx, ma); };
