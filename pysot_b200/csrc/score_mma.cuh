@@ -203,6 +203,7 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 >= 12 ? kMmaMinBlocks - 1 : k
   const int sub = warp & (ma.split - 1);
   const long long base = ((long long)blockIdx.x * ((kMmaThreads / 32) / ma.split) + warp / ma.split) * (8 * kMmaMB);
   const int ntiles = (a.npad + trows - 1) / trows;
+  const bool wlive = base < a.m;  // a warp without a live row only keeps the barriers company
 
   if (tid == 0) {
     for (int s = 0; s < kMmaStages; ++s) mbar_init(&s_full[s], 1);
@@ -282,8 +283,8 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 >= 12 ? kMmaMinBlocks - 1 : k
     const double* tp = s_pts + (size_t)s * trows * ds;
     const double* tw = s_wts + s * trows;
     const double* tn = s_nrm + s * trows;
-    if (base < a.m)
-    for (int j0 = 8 * kMmaJB * sub; j0 < rows; j0 += trows) {  // npad is a multiple of 32 = 8 kMmaJB: tiles are always full
+    const int j0 = 8 * kMmaJB * sub;  // this warp's tile of the stage (npad is a multiple of 32 = 8 kMmaJB: tiles are full)
+    if (wlive && j0 < rows) {
       double acc[kMmaMB][kMmaJB][2];
 #pragma unroll
       for (int i = 0; i < kMmaMB; ++i)
