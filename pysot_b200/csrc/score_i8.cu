@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) score_i8_kernel(I8Args ia) {
   };
   // which pairs are recomputed directly: tiny ones and near ones that can lower the running minimum (score_mma.cuh)
   constexpr int kNearShiftHi = 10 << 20;
-  constexpr int kTinyShiftHi = (KERN == B200RBF_KERNEL_LINEAR ? 10 : 40) << 20;
+  constexpr int kTinyShiftHi = (KERN == B200RBF_KERNEL_LINEAR ? 10 : 26) << 20;
   const int q4 = warp & 3, cg = (warp >> 2) & 3;  // TMEM lane quarter = warp id within the CTA mod 4
   const int crow = 32 * q4 + lane;
   double sum = 0.0;

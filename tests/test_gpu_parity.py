@@ -474,6 +474,52 @@ def test_score_and_gradient_kernels_over_dimension_classes(pb, orc, kernel, tail
     assert np.all(dm[:20] == 0.0) and np.array_equal(idx, tr["picked"])
 
 
+@pytest.mark.parametrize("kernel,tail", [("cubic", "linear"), ("tps", "linear"), ("linear", "constant")])
+@pytest.mark.parametrize("d", [10, 20])
+def test_call_sizes_around_the_center_split_on_a_clustered_cloud(pb, orc, kernel, tail, d):
+    """The DMMA score kernel lets 4 (2) warps share a row group when the call has few rows (up to 7104 / 14208 rows on
+    148 SMs) and recomputes only tiny pairs and near pairs that lower the running minimum.  An optimiser-like cloud
+    (eight tight clusters, radii 1e-6 .. 0.3, duplicates among the candidates) at call sizes on both sides of every
+    boundary, AUG (d = 10) and plain (d = 20) variants, each kernel: values, distances (relative accuracy per
+    candidate) and the pick against the oracle."""
+    rng = np.random.default_rng(7 * d + len(kernel))
+    n, mmax = 700, 14300
+    lb, ub = -2.0 * np.ones(d), 3.0 * np.ones(d)
+    cen = lb + (ub - lb) * rng.random((8, d))
+
+    def cloud(k, lo):
+        which = rng.integers(0, 8, k)
+        rad = 10.0 ** rng.uniform(lo, -0.5, (k, 1)) * (ub - lb)
+        return np.clip(cen[which] + rad * rng.standard_normal((k, d)) / np.sqrt(d), lb, ub)
+
+    X = cloud(n, -6)
+    fX = np.sin(X.sum(1))[:, None]
+    cand = cloud(mmax, -7)
+    o = orc.OracleRBF(d, lb, ub, kernel, tail)
+    o.add_points(X, fX)
+    o.c = rng.standard_normal((n + o.ntail, 1))  # evaluation only: no ill-conditioned fit
+    o.updated = True
+    s = make_gpu(pb, d, lb, ub, kernel, tail)
+    s.add_points(X, fX)
+    s.set_coefficients(o.c)
+    for m in (1, 3, 16, 17, 100, 2000, 7104, 7105, 14208, 14209):
+        q = cand[:m].copy()
+        k = min(m, 5)
+        q[:k] = X[:k]  # coincident with centers: r = 0 exactly
+        assert relmax(s.predict(q), o.predict(q)) < TOL, m
+        tr = {}
+        orc.weighted_distance_merit(1, o, X, fX, q.copy(), [0.5], None, 1e-3, trace=tr)
+        idx, _, fv, dm, _ = pb.merit_select_indices(1, s, X, q, [0.5], None, want_scores=True)
+        ref_d = tr["dmerit0"].ravel()
+        assert relmax(fv, tr["fvals_raw"].ravel()) < TOL, m
+        assert np.all(dm[:k] == 0.0), m
+        if m > k:
+            rel = np.abs(dm - ref_d)[k:] / ref_d[k:]
+            assert rel.max() < 1e-9, (m, rel.max())
+        assert relmax(dm, ref_d) < 1e-12, m
+        assert np.array_equal(idx, tr["picked"]), m
+
+
 # n around the 32 / 128 / 512 blocking of the two-level Cholesky (padding rows, one-block case, last partial panel of
 # an outer panel, first column right of an outer panel)
 @pytest.mark.parametrize("kernel,d,n", [("cubic", 3, 150), ("tps", 10, 1000), ("cubic", 30, 1500), ("tps", 2, 700),
