@@ -143,6 +143,11 @@ int b200rbf_score(b200rbf_handle h, const double* cand, long long m, const doubl
  * idx_out: p selected row indices into cand; merit_out (optional): their merit values. */
 int b200rbf_select(b200rbf_handle h, const double* weights, int p, double dtol, long long* idx_out,
                    double* merit_out);
+/* Same, and also returns the selected rows, new_points = cand[idx] (candidate_srbf.py:51): rows_out (optional) p x d HOST
+ * doubles, delivered by the call's one device-to-host copy -- with device-resident candidates the caller needs no
+ * gather of its own. */
+int b200rbf_select_rows(b200rbf_handle h, const double* weights, int p, double dtol, long long* idx_out,
+                        double* merit_out, double* rows_out);
 
 /* Candidate generation on the device (opt-in; candidate_dycors.py:73-86, candidate_srbf.py:108-113,
  * candidate_uniform.py:44-45, round_vars utils.py:68-93).  kind: 0 DYCORS, 1 SRBF, 2 uniform.  xbest, lb, ub, sigma

@@ -35,6 +35,7 @@ PROTOTYPES = {
     "b200rbf_predict_deriv": (C.c_int, [_vp, _vp, C.c_longlong, _vp, _vp, _vp]),
     "b200rbf_score": (C.c_int, [_vp, _vp, C.c_longlong, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "b200rbf_select": (C.c_int, [_vp, _vp, C.c_int, C.c_double, _vp, _vp]),
+    "b200rbf_select_rows": (C.c_int, [_vp, _vp, C.c_int, C.c_double, _vp, _vp, _vp]),
     "b200rbf_generate": (C.c_int, [_vp, C.c_int, C.c_longlong, C.c_int, _vp, _vp, _vp, _vp, C.c_double, _vp, C.c_int, _vp,
                                    C.c_ulonglong, _vp]),
     "b200rbf_shard_stats": (C.c_int, [_vp, _vp]),
@@ -216,12 +217,16 @@ class Handle:
                                    1 if alias_centers else 0, ptr(fv), ptr(dm), ptr(stats)))
         return fv, dm, stats
 
-    def select(self, weights, num_pts, dtol):
+    def select(self, weights, num_pts, dtol, dim=None):
         w = f64(list(weights)[:num_pts])
         if w.shape[0] < num_pts:
             raise IndexError("list index out of range")  # weights[i] in candidate_srbf.py:45
         idx = np.empty(num_pts, dtype=np.int64)
         merit = np.empty(num_pts)
+        if dim is not None:  # also the selected rows, cand[idx]
+            rows = np.empty((num_pts, dim))
+            check(load().b200rbf_select_rows(self._h, ptr(w), int(num_pts), float(dtol), ptr(idx), ptr(merit), ptr(rows)))
+            return idx, merit, rows
         check(load().b200rbf_select(self._h, ptr(w), int(num_pts), float(dtol), ptr(idx), ptr(merit)))
         return idx, merit
 

@@ -43,11 +43,9 @@ def weighted_distance_merit(num_pts, surrogate, X, fX, cand, weights, Xpend=None
     if not isinstance(surrogate, GpuRBFInterpolant):
         return _reference_or_raise("weighted_distance_merit", surrogate, num_pts=num_pts, surrogate=surrogate, X=X, fX=fX,
                                    cand=cand, weights=weights, Xpend=Xpend, dtol=dtol)
+    if _is_cuda_tensor(cand):  # the selected rows come back with the indices (b200rbf_select_rows): no gather, one copy
+        return merit_select_indices(num_pts, surrogate, X, cand, weights, Xpend, dtol, want_rows=True)[2]
     idx = merit_select_indices(num_pts, surrogate, X, cand, weights, Xpend, dtol)[0]
-    if _is_cuda_tensor(cand):
-        import torch
-
-        return cand[torch.as_tensor(idx, device=cand.device)].cpu().numpy()
     return np.asarray(cand, dtype=np.float64)[idx, :].copy()
 
 
@@ -62,8 +60,9 @@ def _reference_or_raise(name, surrogate_obj, **kw):
                     % (name, type(surrogate_obj).__name__))
 
 
-def merit_select_indices(num_pts, surrogate, X, cand, weights, Xpend=None, dtol=1e-3, want_scores=False):
-    """The device part of weighted_distance_merit.  Returns (indices, merit values[, fvals, dmerit, stats])."""
+def merit_select_indices(num_pts, surrogate, X, cand, weights, Xpend=None, dtol=1e-3, want_scores=False, want_rows=False):
+    """The device part of weighted_distance_merit.  Returns (indices, merit values[, fvals, dmerit, stats]), or with
+    ``want_rows`` (indices, merit values, cand[indices] as a host array)."""
     X = np.asarray(X, dtype=np.float64)
     dim = X.shape[1]
     if _is_cuda_tensor(cand):
@@ -89,6 +88,8 @@ def merit_select_indices(num_pts, surrogate, X, cand, weights, Xpend=None, dtol=
     h = surrogate.handle
     with _torch_stream(h, cand):
         fv, dm, st = h.score(cand, surrogate.lb, surrogate.ub, Xdist, alias, want_scores=want_scores, m=cand.shape[0])
+        if want_rows:
+            return h.select(weights, num_pts, dtol, dim=dim)
         idx, merit = h.select(weights, num_pts, dtol)
     if want_scores:
         return idx, merit, fv, dm, st

@@ -888,23 +888,24 @@ int b200rbf_score(b200rbf_handle h, const double* cand, long long m, const doubl
   return rc;
 }
 
-int b200rbf_select(b200rbf_handle h, const double* weights, int p, double dtol, long long* idx_out,
-                   double* merit_out) {
+int b200rbf_select_rows(b200rbf_handle h, const double* weights, int p, double dtol, long long* idx_out,
+                        double* merit_out, double* rows_out) {
   B2_CHECK(h && weights && idx_out, B200RBF_EINVAL, "NULL argument");
   B2_CHECK(h->score.valid, B200RBF_ESTATE, "nothing scored: call b200rbf_score first");
   B2_CHECK(p >= 1, B200RBF_EINVAL, "num_pts must be >= 1");
   B2_CUDA(cudaSetDevice(h->device));
   ScoreState& S = h->score;
   const Model& M = h->model;
-  B2_TRY(S.results.reserve((size_t)p * 16));
-  B2_TRY(h->pin_small.reserve(((size_t)p * 16 > 4096 * 8) ? (size_t)p * 16 : 4096 * 8));
+  const size_t slot = 16 + (size_t)S.d * 8;  // {merit, index, the selected row}
+  B2_TRY(S.results.reserve((size_t)p * slot));
+  B2_TRY(h->pin_small.reserve(((size_t)p * slot > 4096 * 8) ? (size_t)p * slot : 4096 * 8));
   char* res = reinterpret_cast<char*>(S.results.p);
   for (int i = 0; i < p; ++i) {
     int nb = 0;
     B2_TRY(launch_merit_argmin(h, S.fvals.as<double>(), S.dmerit.as<double>(), S.m, S.stats.as<double>(), 0,
                                weights[i], dtol, 0, S.pair_parts.p, &nb));
     B2_TRY(launch_pick(h, S.pair_parts.p, nb, S.cand, S.d, S.fvals.as<double>(), S.winner.as<double>(), M.dpad,
-                       res + (size_t)i * 16, nullptr));
+                       res + (size_t)i * slot, nullptr));
     if (i + 1 < p) {
       int cnt = 0;
       B2_TRY(launch_update(h, S.cand, S.m, S.d, S.winner.as<double>(), S.dmerit.as<double>(), S.parts.as<double>(),
@@ -912,20 +913,26 @@ int b200rbf_select(b200rbf_handle h, const double* weights, int p, double dtol, 
       B2_TRY(launch_stats(h, S.parts.as<double>(), S.nparts, cnt, 2, S.stats.as<double>()));
     }
   }
-  B2_CUDA(cudaMemcpyAsync(h->pin_small.p, res, (size_t)p * 16, cudaMemcpyDeviceToHost, h->stream));
+  B2_CUDA(cudaMemcpyAsync(h->pin_small.p, res, (size_t)p * slot, cudaMemcpyDeviceToHost, h->stream));
   B2_CUDA(cudaStreamSynchronize(h->stream));
   const char* hp = reinterpret_cast<const char*>(h->pin_small.p);
   for (int i = 0; i < p; ++i) {
     double v;
     long long ix;
-    memcpy(&v, hp + (size_t)i * 16, 8);
-    memcpy(&ix, hp + (size_t)i * 16 + 8, 8);
+    memcpy(&v, hp + (size_t)i * slot, 8);
+    memcpy(&ix, hp + (size_t)i * slot + 8, 8);
     idx_out[i] = ix;
     if (merit_out) merit_out[i] = v;
+    if (rows_out) memcpy(rows_out + (size_t)i * S.d, hp + (size_t)i * slot + 16, (size_t)S.d * 8);
   }
   // the resident scores were consumed (fvals poisoned, dmerit updated): a second select needs a new score
   S.valid = false;
   return 0;
+}
+
+int b200rbf_select(b200rbf_handle h, const double* weights, int p, double dtol, long long* idx_out,
+                   double* merit_out) {
+  return b200rbf_select_rows(h, weights, p, dtol, idx_out, merit_out, nullptr);
 }
 
 int b200rbf_shard_stats(b200rbf_handle h, double* stats_dev) {

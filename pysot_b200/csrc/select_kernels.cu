@@ -161,7 +161,12 @@ __global__ void __launch_bounds__(kSelThreads) pick_kernel(const Pair* __restric
       *result_slot = best;
       fvals[best.i] = d_inf();
     }
-    for (int k = threadIdx.x; k < dpad; k += blockDim.x) winner[k] = k < d ? cand[best.i * (long long)d + k] : 0.0;
+    double* row_out = reinterpret_cast<double*>(result_slot + 1);  // the slot is {merit, index, row[d]}
+    for (int k = threadIdx.x; k < dpad; k += blockDim.x) {
+      const double v = k < d ? cand[best.i * (long long)d + k] : 0.0;
+      winner[k] = v;
+      if (k < d) row_out[k] = v;
+    }
   }
 }
 

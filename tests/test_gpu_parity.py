@@ -342,6 +342,10 @@ def test_large_scoring_against_tiled_oracle(pb, orc):
     assert np.array_equal(fv2, fv) and np.array_equal(dm2, dm) and np.array_equal(idx2, idx)
     out = s.predict_device(ct[:1000])
     assert np.array_equal(out.cpu().numpy().ravel(), fv[:1000])
+    # weighted_distance_merit on the tensor: the rows come back with the indices (b200rbf_select_rows)
+    pts = pb.weighted_distance_merit(4, s, X, None, ct, w, Xpend)
+    assert pts.shape == (4, d) and np.array_equal(pts, cand[idx])
+    assert np.array_equal(pb.weighted_distance_merit(4, s, X, None, cand, w, Xpend), cand[idx])
 
 
 def test_fit_2000_centers_tps(pb, orc):

@@ -295,3 +295,49 @@ def test_fit_decides_between_extension_and_refit():
     plain._handle = StubHandle()
     plain.add_points(X[:20], f[:20]); plain._fit(); plain.add_points(X[20], f[20]); plain._fit()
     assert calls[-2:] == [("fit", 20), ("fit", 21)]
+
+
+def test_add_points_grows_in_place_with_the_reference_bookkeeping():
+    """GpuRBFInterpolant.add_points keeps X / _X / fX as prefixes of geometrically growing buffers and maps only the new
+    rows; the arrays must equal what surrogate.py:50-74 builds (vstack + re-mapping every row), through scalar / 1-d /
+    2-d inputs, growth, pickling, reset() and an outside assignment to X."""
+    import pickle
+
+    import pysot_b200.interface as itf
+    from pysot_b200.rbf import GpuRBFInterpolant
+
+    class Ref(itf._Surrogate):
+        def predict(self, xx):
+            raise NotImplementedError
+
+        def predict_deriv(self, xx):
+            raise NotImplementedError
+
+    d = 5
+    lb, ub = -np.arange(1.0, d + 1), np.arange(2.0, d + 2)
+    ref, gpu = Ref(d, lb, ub), GpuRBFInterpolant(d, lb, ub)
+    rng = np.random.default_rng(0)
+
+    def same(a, b):
+        return (a.num_pts == b.num_pts and np.array_equal(a.X, b.X) and np.array_equal(a._X, b._X)
+                and np.array_equal(a.fX, b.fX) and a.fX.shape == b.fX.shape and not b.updated)
+
+    for k in (1, 3, 1, 1, 70, 1, 200, 1):
+        x, f = lb + (ub - lb) * rng.random((k, d)), rng.random(k)
+        args = (x[0], float(f[0])) if k == 1 else (x, f[:, None] if k == 3 else f)
+        ref.add_points(*args)
+        gpu.add_points(*args)
+        assert same(ref, gpu), k
+    back = pickle.loads(pickle.dumps(gpu))
+    for s in (ref, back):
+        s.add_points(x[0], 1.0)
+    assert same(ref, back)
+    gpu.reset()
+    ref.reset()
+    for s in (ref, gpu):
+        s.add_points(x, f)
+    assert same(ref, gpu)
+    gpu.X = gpu.X.copy()  # someone replaced the array: the buffers are re-seated from what is there
+    for s in (ref, gpu):
+        s.add_points(x, f)
+    assert same(ref, gpu)
