@@ -13,7 +13,7 @@ from conftest import GOLDEN
 out = []
 for name, label in (("trace_dycors.npz", "#1 DYCORS Ackley-10 serial, 500 evals"),
                     ("trace_srbf.npz", "#2 SRBF Levy-30 async x8, 2000 evals"),
-                    ("trace_sop.npz", "#5 SOP Rastrigin-20 8 centers, 600 evals")):
+                    ("trace_sop.npz", "#5 SOP Rastrigin-20 8 centers, 3000 evals")):
     g = np.load(os.path.join(GOLDEN, name))
     ref = float(g["ref_call_seconds"].sum()) if "ref_call_seconds" in g.files else float("nan")
     row = {"config": label, "calls": int(len(g["n"])), "reference_cpu_seconds": ref}
