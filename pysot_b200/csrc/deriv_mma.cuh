@@ -165,9 +165,8 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 >= 9 ? 2 : 3)) deriv_mma_kern
         }
       }
     }
-    // tiny pairs (cold, warp-uniform control flow): the quad forms the direct squared distance together
-    // (quad_exact_r2, score_mma.cuh)
-    if (__any_sync(0xffffffffu, near_any)) {
+    // tiny pairs (rare: duplicates and negative r^2): direct differences, one thread per pair (mma_exact_r2)
+    if (near_any) {
 #pragma unroll
       for (int jb = 0; jb < kMmaJB; ++jb)
 #pragma unroll
@@ -176,16 +175,9 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 >= 9 ? 2 : 3)) deriv_mma_kern
 #pragma unroll
           for (int i = 0; i < kMmaMB; ++i) {
             const int thr = AUG ? max(__double2hiint(nx[i]), __double2hiint(tn[jc])) : __double2hiint(nx[i] + tn[jc]);
-            const bool mine = __double2hiint(acc[i][jb][e]) < thr - kNearShiftHi;
-            const unsigned bal = __ballot_sync(0xffffffffu, mine);
-            if (bal != 0u) {
-#pragma unroll 1
-              for (int src = 0; src < 4; ++src) {
-                if ((bal & (0x11111111u << src)) == 0u) continue;  // no quad has this column flagged
-                const int jsrc = 8 * jb + 2 * src + (e ^ (src >> 1));
-                const double r2x = quad_exact_r2<K4, AUG>(afr[i], a.d, tig, tp + jsrc * ds);
-                if (src == tig && mine) acc[i][jb][e] = r2x;
-              }
+            if (__double2hiint(acc[i][jb][e]) < thr - kNearShiftHi) {
+              const long long row = base + gid + 8 * i;
+              acc[i][jb][e] = mma_exact_r2(a.x + (row < a.m ? row : a.m - 1) * (long long)a.d, a.d, a.lb, a.range, tp + jc * ds);
             }
           }
         }
