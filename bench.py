@@ -506,6 +506,26 @@ def run_native(args, rank, world, local_rank):
         "hbm": {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (k_ms * 1e-3) / 1e9, "peak_gbs": mp["hbm_gbs"],
                 "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / mp["hbm_gbs"], "peak_kind": mp_kind},
     }
+    # the same launch on EXECUTED operations (what ncu's pipe counters see), beside the algorithmic figure above
+    pairs_per_s = float(M_PER_GPU) * N_CENTERS / (k_ms * 1e-3)
+    if which == "int8":
+        kpad = 32 * ((D + 31) // 32)  # int8 k-steps of 32 bytes
+        i8_ops = 26 * kpad * 2        # 26 digit-plane products per pair, multiply + add
+        roofline["executed"] = {
+            "int8_ops_per_pair": i8_ops, "int8_tops": pairs_per_s * i8_ops / 1e12, "int8_nominal_peak_tops": 4500.0,
+            "int8_frac_of_nominal": pairs_per_s * i8_ops / 1e12 / 4500.0,
+            "fp64_ops_per_pair": 12, "fp64_tflops": pairs_per_s * 12 * 2 / 1e12,
+            "fp64_frac": pairs_per_s * 12 * 2 / 1e12 / peaks["dfma_tflops"],
+            "note": "nominal dense int8 peak (no measured int8 figure in MEASURED_PEAKS.json); M128 N64 K32 MMAs complete at "
+                    "27.6 ns each on one SM (tools/umma_rate2.cu) = 19 TMAC/s per SM, i.e. the tensor phase itself runs at "
+                    "the rate the hardware gives this tile shape; FP64 operations counted as FMAs (2 flops); the two "
+                    "phases and the TMEM drain run one after the other (ncu: tensor-core pipe 44 %, ALU 32 %, XU 16 %, "
+                    "FP64 14-24 % busy, summing to ~100 %)"}
+    else:
+        ex = 2 * 4 * ((D + 3) // 4) + 7
+        roofline["executed"] = {"fp64_ops_per_pair": ex, "fp64_tflops": pairs_per_s * ex / 1e12,
+                                "fp64_frac": pairs_per_s * ex / 1e12 / peaks["dfma_tflops"],
+                                "note": "2 x 4 ceil(d / 4) DMMA flops + 7 FP64 operations per pair on the shared datapath"}
     line = {
         "metric": "candidate x center pairs/s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",

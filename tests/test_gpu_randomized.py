@@ -86,6 +86,8 @@ def test_random_case_against_oracle(seed):
     ref_d = tr["dmerit0"].ravel()
     assert relmax(fv, tr["fvals_raw"].ravel()) < 1e-10, tag
     assert np.all(dm[:k] == 0.0), tag
+    idx2, _, fv2, dm2, _ = pb.merit_select_indices(p, s, X, cand, weights, Xpend, dtol, want_scores=True)
+    assert np.array_equal(idx, idx2) and np.array_equal(fv, fv2, equal_nan=True) and np.array_equal(dm, dm2), tag  # run to run: bits
     # per-candidate accuracy of the distance: relative 1e-9, plus the rounding of the unit-box map itself -- with an
     # isotropic box the library derives the distance from the unit-box one (x dscale), and (x - lb) / (ub - lb) rounds
     # each coordinate to eps |u|, i.e. eps * box width in the original space (the reference's cdist subtracts the
