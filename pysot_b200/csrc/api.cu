@@ -1,6 +1,8 @@
 // C ABI of libb200rbf.so (include/b200rbf.h): argument checking, host<->device staging, stream ordering.
 #include <stdarg.h>
 
+#include <thread>
+
 #include "score_mma.cuh"
 
 namespace b200rbf {
@@ -315,6 +317,36 @@ int score_rows(b200rbf_ctx* h, const ScorePlan& plan, const double* cand_dev, lo
   return 0;
 }
 
+// Pageable rows -> pinned staging buffer.  One host thread copies at 5 - 10 GB/s, about the rate at which the score
+// kernel consumes candidates at the bench shape (7 GB/s), so on a slow host the staging bounded the whole call (84 ms
+// for 419 MB against 60 ms of kernels); four threads leave it well under the kernel time.  Short-lived threads: a chunk
+// is >= 8 MB here, the ~0.1 ms of creating them disappears in it, and no pool outlives the call.
+void stage_copy(void* dst, const void* src, size_t bytes) {
+  const size_t kMinParallel = (size_t)8 << 20;
+  unsigned hw = std::thread::hardware_concurrency();
+  const int nt = bytes < kMinParallel ? 1 : (hw >= 8 ? 4 : hw >= 4 ? 2 : 1);
+  if (nt == 1) {
+    memcpy(dst, src, bytes);
+    return;
+  }
+  const size_t slice = ((bytes / nt) + 4095) & ~(size_t)4095;
+  std::thread th[3];
+  int started = 0;
+  for (int i = 1; i < nt; ++i) {
+    const size_t off = slice * i;
+    if (off >= bytes) break;
+    const size_t len = bytes - off < slice ? bytes - off : slice;
+    try {
+      th[started] = std::thread([=] { memcpy(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, len); });
+      ++started;
+    } catch (...) {  // no thread to be had: this slice is copied here
+      memcpy(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, len);
+    }
+  }
+  memcpy(dst, src, slice < bytes ? slice : bytes);
+  for (int i = 0; i < started; ++i) th[i].join();
+}
+
 // stream `m` candidate rows (host or device) through score_rows; host rows are staged chunk by chunk so the
 // H2D copy of chunk i+1 overlaps the kernels of chunk i.  dst_dev receives the rows when they come from the host.
 int score_pipeline(b200rbf_ctx* h, const ScorePlan& plan, const double* cand, long long m, double* dst_dev,
@@ -350,25 +382,33 @@ int score_pipeline(b200rbf_ctx* h, const ScorePlan& plan, const double* cand, lo
   if (kind == kPageable) {
     const long long cr = m < chunk ? m : chunk;
     B2_TRY(h->stage[0].reserve((size_t)cr * row_bytes));
-    if (m > chunk) B2_TRY(h->stage[1].reserve((size_t)cr * row_bytes));
+    if (m > wave_rows) B2_TRY(h->stage[1].reserve((size_t)cr * row_bytes));  // more than one chunk: both buffers alternate
   }
   int off_f = 0, off_d = 0, slot = 0;
   bool used[2] = {false, false};
-  // Pinned source: the chunks grow geometrically from one wave.  Only the first copy is exposed (one wave: 0.3 ms at
-  // the bench shape instead of 0.9 ms), a copy runs ~10x faster than the kernel over the same rows so a chunk twice
-  // the size of the one being scored still lands in time, and fewer launches mean fewer drained last waves.
-  // Pageable source: fixed chunks, bounded by the two staging buffers.
-  long long cur = (kind == kPinned) ? wave_rows : chunk;
+  // The chunks grow geometrically from one wave.  Only the first copy is exposed (one wave: 0.3 ms at the bench shape
+  // instead of 0.9 ms), a copy runs ~10x faster than the kernel over the same rows so a chunk twice the size of the one
+  // being scored still lands in time, and fewer launches mean fewer drained last waves.
+  // Pageable source: the same, up to the size of the two staging buffers (`chunk` rows) -- what is exposed there is the
+  // host memcpy into the staging buffer plus the copy of the FIRST chunk (2.6 + 0.5 ms at a fixed 64k-row chunk).
+  long long cur = wave_rows;
   for (long long r0 = 0, rows = 0; r0 < m; r0 += rows, slot ^= 1) {
     rows = (m - r0 < cur) ? (m - r0) : cur;
     if (kind == kPinned) {
       if (m - r0 - rows < wave_rows) rows = m - r0;  // no sub-wave remainder launch
       cur *= 2;
+    } else {
+      if (m - r0 - rows < wave_rows && m - r0 <= chunk) rows = m - r0;
+      // x1.5 (whole waves), not x2: staging the NEXT chunk (one host thread, ~10 GB/s) must not take longer than the
+      // kernel over the current one (~7 GB/s of candidates at the bench shape), or the GPU waits for the host
+      long long nxt = cur + (cur / (2 * wave_rows)) * wave_rows;
+      if (nxt == cur) nxt = cur + wave_rows;
+      cur = nxt < chunk ? nxt : chunk;
     }
     const void* src = cand + r0 * M.d;
     if (kind == kPageable) {
       if (used[slot]) B2_CUDA(cudaEventSynchronize(h->ev_copy[slot]));  // staging buffer free again
-      memcpy(h->stage[slot].p, src, (size_t)rows * row_bytes);
+      stage_copy(h->stage[slot].p, src, (size_t)rows * row_bytes);
       src = h->stage[slot].p;
     }
     B2_CUDA(cudaMemcpyAsync(dst_dev + r0 * M.d, src, (size_t)rows * row_bytes, cudaMemcpyHostToDevice,

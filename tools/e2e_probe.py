@@ -17,7 +17,7 @@ cand = rng.random((m, d))
 pin = torch.from_numpy(cand).pin_memory()
 cand_pin = pin.numpy()
 dev = pin.cuda()
-def run(c, reps=4):
+def run(c, reps=8):
     best = 1e9
     for _ in range(reps):
         torch.cuda.synchronize(); t0 = time.perf_counter()
@@ -25,6 +25,6 @@ def run(c, reps=4):
         torch.cuda.synchronize(); best = min(best, time.perf_counter() - t0)
     return best * 1e3
 print("device-resident: %.2f ms (kernel %.2f ms)" % (run(dev), h.last_score_ms))
-for chunk in (0, 32768, 65536, 131072, 262144, 524288):
+for chunk in (0, 16384, 32768, 50000, 65536, 131072):
     if chunk: h.set_option(_lib.OPT_CHUNK_ROWS, chunk)
     print("chunk_rows %7s: pinned host %.2f ms (kernels %.2f ms)   pageable host %.2f ms" % (chunk or "default", run(cand_pin), h.last_score_ms, run(cand)))
