@@ -517,8 +517,9 @@ def run_native(args, rank, world, local_rank):
             "fp64_ops_per_pair": 12, "fp64_tflops": pairs_per_s * 12 * 2 / 1e12,
             "fp64_frac": pairs_per_s * 12 * 2 / 1e12 / peaks["dfma_tflops"],
             "note": "nominal dense int8 peak (no measured int8 figure in MEASURED_PEAKS.json); M128 N64 K32 MMAs complete at "
-                    "27.6 ns each on one SM (tools/umma_rate2.cu) = 19 TMAC/s per SM, i.e. the tensor phase itself runs at "
-                    "the rate the hardware gives this tile shape; FP64 operations counted as FMAs (2 flops); the two "
+                    "27.6 ns each on one SM (tools/umma_rate2.cu) = 9.5 TMAC/s = 19 TOPS per SM, 62 % of the nominal peak: the "
+                    "per-instruction floor for N <= 64 (N = 128 would need 896 of the 512 TMEM columns for the seven "
+                    "accumulators), and the tensor phase is 42 % of the tile time; FP64 operations counted as FMAs (2 flops); the two "
                     "phases and the TMEM drain run one after the other (ncu: tensor-core pipe 44 %, ALU 32 %, XU 16 %, "
                     "FP64 14-24 % busy, summing to ~100 %)"}
     else:
