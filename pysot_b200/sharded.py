@@ -169,8 +169,10 @@ def sharded_weighted_distance_merit(num_pts, surrogate, X, fX, cand_local, weigh
     X = np.asarray(X, dtype=np.float64)
     if Xpend is None:
         Xpend = np.empty([0, X.shape[1]])
-    Xdist = np.vstack((X, Xpend))
     surrogate._fit()
-    alias = X.shape == surrogate.X.shape and np.array_equal(X, surrogate.X)
+    from .candidates import dist_points, same_points
+
+    alias = same_points(X, surrogate.X)
+    Xdist = dist_points(surrogate, X, Xpend, alias)
     idx, rows = sharded_select(GpuShardBackend(surrogate), cand_local, Xdist, alias, weights, num_pts, dtol, group, offset)
     return rows, idx
