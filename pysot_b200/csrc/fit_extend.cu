@@ -252,18 +252,37 @@ __global__ void __launch_bounds__(kExtRows) ext_row_a_kernel(const double* __res
   scol[tid] = base ? col : 0.0;
   sg[tid] = base ? g : 0.0;
   __syncthreads();
+  // per-CTA partial sums over this CTA's base rows, thread = (row group, column): 8 groups x 32 columns walk the rows
+  // 8 apart (coalesced across the columns of a Q row), then the groups are added in a fixed order.  (The first version
+  // gave each of the tp <= 32 columns one thread walking all 256 rows: ~100 us of dependent L2 loads per extension,
+  // the largest single item of the 0.3 ms at n = 2700.)
   const int r0 = blockIdx.x * kExtRows;
-  if (r0 < n0) {
+  if (r0 < n0) {  // block-uniform
     const int rows = min(kExtRows, n0 - r0);
-    for (int a = tid; a < tp; a += kExtRows) {
+    double* red = sg + kExtRows;  // 2 x 8 x 32
+    const int cl = tid & 31, rg = tid >> 5;
+    for (int a0 = 0; a0 < tp; a0 += 32) {
+      const int a = a0 + cl;
       double sw = 0.0, ss = 0.0;
-      for (int r = 0; r < rows; ++r) {
-        const double q = Qx[(size_t)(r0 + r) * tp + a];
-        sw = fma(q, scol[r], sw);
-        ss = fma(q, sg[r], ss);
+      if (a < tp)
+        for (int r = rg; r < rows; r += kExtRows / 32) {
+          const double q = Qx[(size_t)(r0 + r) * tp + a];
+          sw = fma(q, scol[r], sw);
+          ss = fma(q, sg[r], ss);
+        }
+      red[rg * 32 + cl] = sw;
+      red[kExtRows + rg * 32 + cl] = ss;
+      __syncthreads();
+      if (tid < 32 && a < tp) {
+        double w = 0.0, s2 = 0.0;
+        for (int g = 0; g < kExtRows / 32; ++g) {
+          w += red[g * 32 + tid];
+          s2 += red[kExtRows + g * 32 + tid];
+        }
+        part[((size_t)blockIdx.x * 2 + 0) * tp + a] = w;
+        part[((size_t)blockIdx.x * 2 + 1) * tp + a] = s2;
       }
-      part[((size_t)blockIdx.x * 2 + 0) * tp + a] = sw;
-      part[((size_t)blockIdx.x * 2 + 1) * tp + a] = ss;
+      __syncthreads();
     }
   }
 }
@@ -486,7 +505,7 @@ int chol_extend_weights(b200rbf_ctx* h, const double* f_dev, int n, bool rhs_cha
   if (rhs_changed) B2_TRY(ext_refresh_rhs(h, f_dev));
   for (int j = E.N; j < n; ++j) {
     const int ctas = (j + 1 + kExtRows - 1) / kExtRows;
-    const size_t sm_a = ((size_t)d + 2 * (size_t)w.tp + 2 * kExtRows) * sizeof(double), sm_b = 3 * (size_t)w.tp * sizeof(double);
+    const size_t sm_a = ((size_t)d + 2 * (size_t)w.tp + 4 * kExtRows) * sizeof(double), sm_b = 3 * (size_t)w.tp * sizeof(double);
     ext_row_a_kernel<<<ctas, kExtRows, sm_a, h->stream>>>(E.Xu.as<double>(), d, E.n0, j, E.kernel, E.eta, w.Rinv, w.t, w.tp, w.P,
                                                           w.W, w.gbuf, w.part, h->exact_dist ? 1 : 0);
     LAUNCHED(h);
