@@ -1,7 +1,7 @@
 // Device-side candidate generation: the perturbation half of candidate_dycors / candidate_srbf /
 // candidate_uniform without the host.  On the CPU scipy.stats.truncnorm.rvs is ~50 % of candidate_dycors at d = 10 and
-// makes BASELINE config #4 host-bound (64 M x 50 candidates take minutes to draw and 25 GB to ship); here a row is a
-// few hundred Philox rounds.  OPT-IN: the streams differ from numpy's / scipy's, so a seeded run does not reproduce the
+// makes BASELINE config #4 host-bound (64 M x 50 candidates take minutes to draw and 25 GB to ship); here a row is one
+// warp's worth of Philox rounds and inverse-CDF evaluations.  OPT-IN: the streams differ from numpy's / scipy's, so a seeded run does not reproduce the
 // reference's candidate SETS -- the distributions are the same (tests/test_gpu_generate.py: KS tests, mask statistics).
 //
 //   DYCORS  (candidate_dycors.py:73-86): coordinate j of `subset` is perturbed with probability prob_perturb; a row with
@@ -58,50 +58,79 @@ struct GenArgs {
   double* cand;  // m x d
 };
 
-__global__ void __launch_bounds__(128) generate_kernel(GenArgs a) {
-  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= a.m) return;
+// One WARP per row, lane = coordinate of `subset` (round 2; the first version gave a row to one thread, which walked its
+// coordinates one after the other: a strategy's 100 d rows are two dozen CTAs and d sequential inverse-CDF
+// evaluations, 45 us at d = 30 -- the largest kernel of a proposal).  The CDF bounds of the truncation depend on the
+// coordinate only and are computed once per CTA.  Counter-based RNG: the values are those of the first version, bit
+// for bit.
+constexpr int kGenWarps = 8;        // rows in flight per CTA
+constexpr int kGenRowsPerWarp = 2;  // rows a warp handles one after the other
+__global__ void __launch_bounds__(32 * kGenWarps) generate_kernel(GenArgs a) {
+  extern __shared__ double gs[];
+  double* s_ca = gs;           // nsub: Phi((lb - xbest) / sigma)
+  double* s_cb = gs + a.nsub;  // nsub: Phi((ub - xbest) / sigma)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (a.kind != 2) {
+    for (int j = threadIdx.x; j < a.nsub; j += blockDim.x) {
+      const int k = a.subset[j];
+      const double xb = a.xbest[k], s = a.sigma[k];
+      s_ca[j] = normcdf((a.lb[k] - xb) / s);
+      s_cb[j] = normcdf((a.ub[k] - xb) / s);
+    }
+  }
+  __syncthreads();
   Philox rng{(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
-  double* out = a.cand + row * a.d;
-  for (int k = 0; k < a.d; ++k) out[k] = a.xbest[k];  // np.multiply(np.ones((num_cand, dim)), xbest)
-  int forced = -1;
-  if (a.kind == 0 && a.nsub > 1) {
-    // does any coordinate get perturbed?  (first uniform of every draw is the mask decision)
-    bool any = false;
-    for (int j = 0; j < a.nsub && !any; ++j) {
+  for (int rr = 0; rr < kGenRowsPerWarp; ++rr) {
+    const long long row = ((long long)blockIdx.x * kGenWarps + warp) * kGenRowsPerWarp + rr;
+    if (row >= a.m) break;  // warp-uniform
+    double* out = a.cand + row * a.d;
+    for (int k = lane; k < a.d; k += 32) out[k] = a.xbest[k];  // np.multiply(np.ones((num_cand, dim)), xbest)
+    __syncwarp();  // a perturbed coordinate may be written by another lane than the one that filled it
+    int forced = -1;
+    if (a.kind == 0 && a.nsub > 1) {
+      // does any coordinate get perturbed?  (first uniform of every draw is the mask decision)
+      bool any = false;
+      for (int j0 = 0; j0 < a.nsub; j0 += 32) {
+        const int j = j0 + lane;
+        bool mine = false;
+        if (j < a.nsub) {
+          double u0, u1;
+          rng.draw((unsigned long long)row, (uint32_t)j, u0, u1);
+          mine = u0 < a.prob_perturb;
+        }
+        any |= __any_sync(0xffffffffu, mine);
+      }
+      if (!any) {
+        double u0, u1;
+        rng.draw((unsigned long long)row, 0x80000000u, u0, u1);
+        forced = min((int)(u0 * (a.nsub - 1)), a.nsub - 2);  // np.random.randint(0, len(subset) - 1): last one never chosen
+      }
+    }
+    for (int j = lane; j < a.nsub; j += 32) {
+      const int k = a.subset[j];
       double u0, u1;
       rng.draw((unsigned long long)row, (uint32_t)j, u0, u1);
-      any = u0 < a.prob_perturb;
+      const double lo = a.lb[k], hi = a.ub[k];
+      double x;
+      if (a.kind == 2) {
+        x = lo + (hi - lo) * u1;  // np.random.uniform(lb, ub)
+      } else {
+        const bool perturb = a.kind == 1 || a.nsub == 1 || u0 < a.prob_perturb || j == forced;
+        if (!perturb) continue;
+        const double xb = a.xbest[k], s = a.sigma[k];
+        // truncnorm(a=(lo-xb)/s, b=(hi-xb)/s, loc=xb, scale=s) by inverse CDF; lo <= xb <= hi so 0 is inside [a, b]
+        const double ca = s_ca[j], cb = s_cb[j];
+        x = xb + s * normcdfinv(ca + u1 * (cb - ca));
+        x = fmin(fmax(x, lo), hi);
+      }
+      if (a.int_mask != nullptr && a.int_mask[k]) x = fmin(fmax(rint(x), lo), hi);  // np.round (half to even) + clip
+      out[k] = x;
     }
-    if (!any) {
-      double u0, u1;
-      rng.draw((unsigned long long)row, 0x80000000u, u0, u1);
-      forced = min((int)(u0 * (a.nsub - 1)), a.nsub - 2);  // np.random.randint(0, len(subset) - 1): last one never chosen
+    if (a.int_mask != nullptr) {  // round_vars also rounds untouched integer coordinates (xbest is integral already)
+      __syncwarp();
+      for (int k = lane; k < a.d; k += 32)
+        if (a.int_mask[k]) out[k] = fmin(fmax(rint(out[k]), a.lb[k]), a.ub[k]);
     }
-  }
-  for (int j = 0; j < a.nsub; ++j) {
-    const int k = a.subset[j];
-    double u0, u1;
-    rng.draw((unsigned long long)row, (uint32_t)j, u0, u1);
-    const double lo = a.lb[k], hi = a.ub[k];
-    double x;
-    if (a.kind == 2) {
-      x = lo + (hi - lo) * u1;  // np.random.uniform(lb, ub)
-    } else {
-      const bool perturb = a.kind == 1 || a.nsub == 1 || u0 < a.prob_perturb || j == forced;
-      if (!perturb) continue;
-      const double xb = a.xbest[k], s = a.sigma[k];
-      // truncnorm(a=(lo-xb)/s, b=(hi-xb)/s, loc=xb, scale=s) by inverse CDF; lo <= xb <= hi so 0 is inside [a, b]
-      const double ca = normcdf((lo - xb) / s), cb = normcdf((hi - xb) / s);
-      x = xb + s * normcdfinv(ca + u1 * (cb - ca));
-      x = fmin(fmax(x, lo), hi);
-    }
-    if (a.int_mask != nullptr && a.int_mask[k]) x = fmin(fmax(rint(x), lo), hi);  // np.round (half to even) + clip
-    out[k] = x;
-  }
-  if (a.int_mask != nullptr) {  // round_vars also rounds untouched integer coordinates (xbest is integral already)
-    for (int k = 0; k < a.d; ++k)
-      if (a.int_mask[k]) out[k] = fmin(fmax(rint(out[k]), a.lb[k]), a.ub[k]);
   }
 }
 
@@ -139,7 +168,8 @@ int run_generate(b200rbf_ctx* h, int kind, long long m, int d, const double* xbe
   a.subset = reinterpret_cast<int*>(dp + 4 * nd * sizeof(double));
   a.int_mask = any_int ? reinterpret_cast<unsigned char*>(dp + 4 * nd * sizeof(double) + (size_t)nsub * sizeof(int)) : nullptr;
   a.prob_perturb = prob_perturb; a.seed = seed; a.cand = cand_dev;
-  generate_kernel<<<(unsigned)((m + 127) / 128), 128, 0, h->stream>>>(a);
+  const long long rows_per_cta = kGenWarps * kGenRowsPerWarp;
+  generate_kernel<<<(unsigned)((m + rows_per_cta - 1) / rows_per_cta), 32 * kGenWarps, 2 * (size_t)nsub * sizeof(double), h->stream>>>(a);
   h->launches++;
   B2_CUDA(cudaGetLastError());
   return 0;
