@@ -210,12 +210,16 @@ bool use_i8(const b200rbf_ctx* h, bool with_phi) {
                     (h->i8_dist < 0 && (dd > 64 || (h->cur_m >= 8192 && (dd >= 36 || (dd >= 28 && dd <= 32)))));
   return with_phi && want && h->mma_dist && !h->i8_veto && !h->model.i8_bad && !h->exact_dist && h->model.d <= 128;
 }
-// DMMA score kernel, few candidates: 2 or 4 warps share a 16-row group and split the centers between them, so that a
-// strategy-sized call (100 d candidates) fills the SMs: 16-row groups x split <= ~1 CTA slot in 3 per SM
+// DMMA score kernel, few candidates: 4 (2) warps share a 16-row group and split the centers between them -- as long as
+// that leaves at most ONE CTA per SM.  A call this small is latency-bound per warp, so two CTAs on an SM take twice as
+// long per stage as one, and the kernel ends with the slowest SM: 3000 rows (188 groups) ran 46 us at split 4 (188 CTAs
+// on 148 SMs) and 40 us at split 2 (94 CTAs).
 int mma_split(const b200rbf_ctx* h) {
   const long long groups = (h->cur_m + 8 * kMmaMB - 1) / (8 * kMmaMB);
-  const long long warps = (long long)h->sm_count * 12;
-  return groups * 4 <= warps ? 4 : groups * 2 <= warps ? 2 : 1;
+  const int per_cta = kMmaRowsPerCta / (8 * kMmaMB);  // row groups of a CTA at split 1
+  for (int s = per_cta; s > 1; s >>= 1)
+    if ((groups * s + per_cta - 1) / per_cta <= h->sm_count) return s;
+  return 1;
 }
 // candidates per CTA of the kernel that computes surrogate values / of the distance-only kernel
 int main_rows(const b200rbf_ctx* h) {

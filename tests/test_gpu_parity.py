@@ -481,8 +481,8 @@ def test_score_and_gradient_kernels_over_dimension_classes(pb, orc, kernel, tail
 @pytest.mark.parametrize("kernel,tail", [("cubic", "linear"), ("tps", "linear"), ("linear", "constant")])
 @pytest.mark.parametrize("d", [10, 20])
 def test_call_sizes_around_the_center_split_on_a_clustered_cloud(pb, orc, kernel, tail, d):
-    """The DMMA score kernel lets 4 (2) warps share a row group when the call has few rows (up to 7104 / 14208 rows on
-    148 SMs) and recomputes only tiny pairs and near pairs that lower the running minimum.  An optimiser-like cloud
+    """The DMMA score kernel lets 4 (2) warps share a row group when the call has few rows (up to 2368 / 4736 rows on
+    148 SMs: at most one CTA per SM) and recomputes only tiny pairs and near pairs that lower the running minimum.  An optimiser-like cloud
     (eight tight clusters, radii 1e-6 .. 0.3, duplicates among the candidates) at call sizes on both sides of every
     boundary, AUG (d = 10) and plain (d = 20) variants, each kernel: values, distances (relative accuracy per
     candidate) and the pick against the oracle."""
@@ -506,7 +506,7 @@ def test_call_sizes_around_the_center_split_on_a_clustered_cloud(pb, orc, kernel
     s = make_gpu(pb, d, lb, ub, kernel, tail)
     s.add_points(X, fX)
     s.set_coefficients(o.c)
-    for m in (1, 3, 16, 17, 100, 2000, 7104, 7105, 14208, 14209):
+    for m in (1, 3, 16, 17, 100, 2000, 2368, 2369, 4736, 4737, 7105, 14209):
         q = cand[:m].copy()
         k = min(m, 5)
         q[:k] = X[:k]  # coincident with centers: r = 0 exactly
