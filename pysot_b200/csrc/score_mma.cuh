@@ -223,22 +223,36 @@ __global__ void __launch_bounds__(kMmaThreads, (K4 >= 12 ? kMmaMinBlocks - 1 : k
     for (int t = 0; t < kMmaStages && t < ntiles; ++t) issue(t);
 
   // A fragments: shifted unit-box coordinates of candidates base + gid + 8 i, dimensions 4 k + tig
+  // All global loads first, then the unit-box divisions: an IEEE division is a call (slow path), the compiler does not
+  // move loads across it, and load -> divide -> load -> divide ... cost one memory latency per coordinate -- 2 K4 of them
+  // per thread, ~12 us of the ~17 us a one-stage call took (ncu source view of a one-point predict()).
   double afr[kMmaMB][K4];
   double nx[kMmaMB];
+  double lbv[K4], rgv[K4];
+#pragma unroll
+  for (int k = 0; k < K4; ++k) {
+    const int dim = 4 * k + tig;
+    const bool ok = dim < a.d && a.lb != nullptr;
+    lbv[k] = ok ? __ldg(a.lb + dim) : 0.0;
+    rgv[k] = ok ? __ldg(a.range + dim) : 1.0;
+  }
 #pragma unroll
   for (int i = 0; i < kMmaMB; ++i) {
     const long long row = base + gid + 8 * i;
     const double* src = a.cand + (row < a.m ? row : a.m - 1) * (long long)a.d;
     const bool live = row < a.m;  // rows past the end compute on the unit-box origin: copies of row m - 1 would repeat
-    double n2 = 0.0;              // its near-pair work 15 times over in a one-point predict()
+#pragma unroll                    // its near-pair work 15 times over in a one-point predict()
+    for (int k = 0; k < K4; ++k) afr[i][k] = (4 * k + tig < a.d && live) ? __ldg(src + 4 * k + tig) : 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < kMmaMB; ++i) {
+    const bool live = base + gid + 8 * i < a.m;
+    double n2 = 0.0;
 #pragma unroll
     for (int k = 0; k < K4; ++k) {
       const int dim = 4 * k + tig;
-      double v = 0.0;
-      if (dim < a.d && live) {
-        v = __ldg(src + dim);
-        if (a.lb != nullptr) v = __ddiv_rn(__dsub_rn(v, __ldg(a.lb + dim)), __ldg(a.range + dim));
-      }
+      double v = afr[i][k];
+      if (dim < a.d && live && a.lb != nullptr) v = __ddiv_rn(__dsub_rn(v, lbv[k]), rgv[k]);
       afr[i][k] = AUG ? -2.0 * v : v;
       n2 = fma(v, v, n2);
     }
